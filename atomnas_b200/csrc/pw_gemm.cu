@@ -1,0 +1,707 @@
+// Pointwise (1x1) convolutions of the AtomNAS atomic block as tcgen05 tensor-core GEMMs.
+//
+//   pw_gemm_kernel  : D[M,N] = Aeff[M,K] * W[N,K]^T        (forward conv, and dgrad with W^T)
+//   pw_wgrad_kernel : dW[cb,cs] = sum_m Peff[m,cb] * q[m,cs] (weight gradient, contraction over
+//                     pixels, both operands MN-major straight out of the NHWC activations)
+//
+// Reference call sites replaced: nn.Conv2d(k=1) in ConvBNReLU (models/mobilenet_base.py:135-141,
+// used at :315-320), the linear projection (:338) with the python branch `sum` (:378), the head
+// conv (models/mobilenet_supernet.py:148-153) and nn.Linear (:160-163), plus their autograd
+// backward.  Training-mode BatchNorm (:142, :342) is split around the GEMM: the producer layer's
+// BN-apply + activation runs as a prologue on the A tile in shared memory, the statistics of this
+// layer's output are reduced in the epilogue (see DESIGN.md "kernel pattern").
+//
+// Structure (both kernels): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread
+// tcgen05.mma issuer, warps 2-5 = operand prologue (in-place transform of the 128B-swizzled
+// tile), warps 6-9 = epilogue (tcgen05.ld -> registers -> global).  mbarrier pipelines:
+// full/xf/empty per smem stage, tfull/tempty per TMEM accumulator buffer.
+#include "common.cuh"
+#include "../../include/atomnas_b200.h"
+
+namespace an {
+
+constexpr int kBM = 128;            // rows (pixels) per tile == UMMA M
+constexpr int kBK = 64;             // bf16 elements per 128-byte swizzle row
+constexpr int kMaxBN = 128;         // max UMMA N of the forward/dgrad kernel
+constexpr int kTileA = kBM * kBK * 2;      // 16 KiB
+constexpr int kTileB = kMaxBN * kBK * 2;   // 16 KiB
+constexpr int kThreads = 320;
+constexpr int kMaxGroupCols = 1024;        // columns whose BN partials one CTA keeps in smem
+constexpr int kTmemCols = 256;             // 2 accumulator buffers x 128 columns
+constexpr int kAuxBytes = 256 + 4 * 2 * kMaxBN * 4 + 2 * kMaxGroupCols * 4;
+
+struct GemmDev {
+  CUtensorMap tm_x1, tm_x2, tm_w;
+  int M, N, K;
+  int block_n, stages, m_tiles, n_tiles, tiles_per_group;
+  int a_mode, a_act;
+  const float *a1, *a2, *a3;
+  int epi_mode;
+  void* y;
+  long long ldy;
+  int y_is_f32;
+  const float* bias;
+  float* stats_part;
+  const __nv_bfloat16* r;
+  long long ldr;
+  const float *r_scale, *r_shift, *r_mean, *r_rstd;
+  int r_act;
+};
+
+// 8 consecutive channels of a per-channel coefficient vector (zero beyond `limit`).
+__device__ __forceinline__ void load_coef8(const float* p, int ch, int limit, float* out,
+                                           float fill) {
+  if (p != nullptr && ch < limit) {
+    const float4 lo = __ldg(reinterpret_cast<const float4*>(p + ch));
+    const float4 hi = __ldg(reinterpret_cast<const float4*>(p + ch + 4));
+    out[0] = lo.x; out[1] = lo.y; out[2] = lo.z; out[3] = lo.w;
+    out[4] = hi.x; out[5] = hi.y; out[6] = hi.z; out[7] = hi.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) out[i] = fill;
+  }
+}
+
+// In-place prologue on one 16-byte chunk (8 channels) of a swizzled operand tile.
+__device__ __forceinline__ uint4 transform_chunk(uint4 v, uint4 w, int mode, int act,
+                                                 const float* c1, const float* c2,
+                                                 const float* c3) {
+  const uint32_t vi[4] = {v.x, v.y, v.z, v.w};
+  const uint32_t wi[4] = {w.x, w.y, w.z, w.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float lo = fmaf(c1[2 * i], bf16_lo(vi[i]), c3[2 * i]);
+    float hi = fmaf(c1[2 * i + 1], bf16_hi(vi[i]), c3[2 * i + 1]);
+    if (mode == 2) {
+      lo = fmaf(c2[2 * i], bf16_lo(wi[i]), lo);
+      hi = fmaf(c2[2 * i + 1], bf16_hi(wi[i]), hi);
+    } else {
+      lo = act_fwd(lo, act);
+      hi = act_fwd(hi, act);
+    }
+    o[i] = pack_bf16(lo, hi);
+  }
+  return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) pw_gemm_kernel(const __grid_constant__ GemmDev p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = p.stages;
+  const int a_bytes = (p.a_mode == 2) ? 2 * kTileA : kTileA;
+  const int stage_bytes = a_bytes + kTileB;
+  uint8_t* aux = smem + S * stage_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(aux);
+  uint64_t* xf = full + 8;
+  uint64_t* empty = xf + 8;
+  uint64_t* tfull = empty + 8;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* stat_warp = reinterpret_cast<float*>(aux + 256);   // [4][2][kMaxBN]
+  float* stat_acc = stat_warp + 4 * 2 * kMaxBN;             // [2][kMaxGroupCols]
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tm_x1);
+    tma_prefetch_desc(&p.tm_w);
+    if (p.a_mode == 2) tma_prefetch_desc(&p.tm_x2);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < S; ++s) {
+        mbar_init(&full[s], 1);
+        mbar_init(&xf[s], 128);
+        mbar_init(&empty[s], 1);
+      }
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(&tfull[b], 1);
+        mbar_init(&tempty[b], 128);
+      }
+      mbar_fence_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, kTmemCols);
+  }
+  for (int i = threadIdx.x; i < 2 * kMaxGroupCols; i += kThreads) stat_acc[i] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int nt_begin = blockIdx.y * p.tiles_per_group;
+  const int nt_end = min(p.n_tiles, nt_begin + p.tiles_per_group);
+  const int kblocks = (p.K + kBK - 1) / kBK;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      const uint32_t tx = static_cast<uint32_t>(a_bytes + p.block_n * 128);
+      for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x)
+        for (int nt = nt_begin; nt < nt_end; ++nt)
+          for (int kb = 0; kb < kblocks; ++kb, ++it) {
+            const int s = it % S;
+            const uint32_t ph = (it / S) & 1;
+            mbar_wait(&empty[s], ph ^ 1);
+            mbar_expect_tx(&full[s], tx);
+            uint8_t* st = smem + s * stage_bytes;
+            tma_load_2d(st, &p.tm_x1, &full[s], kb * kBK, mt * kBM);
+            if (p.a_mode == 2) tma_load_2d(st + kTileA, &p.tm_x2, &full[s], kb * kBK, mt * kBM);
+            tma_load_2d(st + a_bytes, &p.tm_w, &full[s], kb * kBK, nt * p.block_n);
+          }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      uint32_t it = 0, tc = 0;
+      const uint32_t idesc = umma_idesc_bf16(kBM, p.block_n, 0, 0);
+      for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x)
+        for (int nt = nt_begin; nt < nt_end; ++nt, ++tc) {
+          const uint32_t buf = tc & 1, tph = (tc >> 1) & 1;
+          mbar_wait(&tempty[buf], tph ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * kMaxBN;
+          for (int kb = 0; kb < kblocks; ++kb, ++it) {
+            const int s = it % S;
+            const uint32_t ph = (it / S) & 1;
+            mbar_wait(&full[s], ph);
+            if (p.a_mode != 0) mbar_wait(&xf[s], ph);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
+            const uint32_t b_addr = a_addr + a_bytes;
+            const int nk = min(4, (p.K - kb * kBK + 15) / 16);
+            for (int k = 0; k < nk; ++k)
+              umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32, 16, 1024),
+                        umma_desc_sw128(b_addr + k * 32, 16, 1024), idesc,
+                        (kb > 0 || k > 0) ? 1u : 0u);
+            umma_commit(&empty[s]);
+            if (kb == kblocks - 1) umma_commit(&tfull[buf]);
+          }
+        }
+    }
+  } else if (warp < 6) {
+    // ------------------------------------------------------------------ A-operand prologue
+    if (p.a_mode != 0) {
+      const int t = threadIdx.x - 64;
+      const int cp = t & 7, r0 = t >> 3;
+      const int cl = cp ^ (r0 & 7);            // logical 16B chunk held at physical chunk cp
+      uint32_t it = 0;
+      for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x)
+        for (int nt = nt_begin; nt < nt_end; ++nt)
+          for (int kb = 0; kb < kblocks; ++kb, ++it) {
+            const int s = it % S;
+            const uint32_t ph = (it / S) & 1;
+            const int kch = kb * kBK + cl * 8;
+            float c1[8], c2[8], c3[8];
+            load_coef8(p.a1, kch, p.K, c1, 0.f);
+            load_coef8(p.a3, kch, p.K, c3, 0.f);
+            if (p.a_mode == 2) load_coef8(p.a2, kch, p.K, c2, 0.f);
+            mbar_wait(&full[s], ph);
+            uint8_t* a = smem + s * stage_bytes + r0 * 128 + cp * 16;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              uint4* ptr = reinterpret_cast<uint4*>(a + i * 16 * 128);
+              const uint4 v = *ptr;
+              uint4 w = make_uint4(0, 0, 0, 0);
+              if (p.a_mode == 2) w = *reinterpret_cast<const uint4*>(a + i * 16 * 128 + kTileA);
+              *ptr = transform_chunk(v, w, p.a_mode, p.a_act, c1, c2, c3);
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(&xf[s]);
+          }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue
+    const int q = warp & 3;                    // TMEM lane quarter this warp may access
+    const int et = q * 32 + lane;              // row within the tile
+    const bool want_stats = p.stats_part != nullptr;
+    const int nchunks = p.block_n / 16;
+    uint32_t tc = 0;
+    for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x)
+      for (int nt = nt_begin; nt < nt_end; ++nt, ++tc) {
+        const uint32_t buf = tc & 1, tph = (tc >> 1) & 1;
+        const long long row = static_cast<long long>(mt) * kBM + et;
+        const bool row_ok = row < p.M;
+        const int ncol0 = nt * p.block_n;
+        uint4 rr[16];
+        if (p.epi_mode != 0) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int col = ncol0 + j * 8;
+            rr[j] = make_uint4(0, 0, 0, 0);
+            if (p.r != nullptr && j < 2 * nchunks && row_ok && col < p.N)
+              rr[j] = ldg_nc_v4(p.r + row * p.ldr + col);
+          }
+        }
+        mbar_wait(&tfull[buf], tph);
+        tc_fence_after();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (j < nchunks) {
+            float v[16];
+            tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kMaxBN + j * 16, v);
+            const int col0 = ncol0 + j * 16;
+            float s1[16], s2[16];
+            if (p.epi_mode == 0) {
+              if (p.bias != nullptr) {
+#pragma unroll
+                for (int c = 0; c < 16; ++c)
+                  if (col0 + c < p.N) v[c] += __ldg(p.bias + col0 + c);
+              }
+              if (!p.y_is_f32) {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) v[c] = round_bf16(v[c]);
+              }
+#pragma unroll
+              for (int c = 0; c < 16; ++c) {
+                const float x = (row_ok && col0 + c < p.N) ? v[c] : 0.f;
+                s1[c] = x;
+                s2[c] = x * x;
+              }
+            } else {
+              const uint32_t ri[8] = {rr[2 * j].x,     rr[2 * j].y,     rr[2 * j].z,
+                                      rr[2 * j].w,     rr[2 * j + 1].x, rr[2 * j + 1].y,
+                                      rr[2 * j + 1].z, rr[2 * j + 1].w};
+              float rv[16];
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                rv[2 * c] = bf16_lo(ri[c]);
+                rv[2 * c + 1] = bf16_hi(ri[c]);
+              }
+              if (p.epi_mode == 1) {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                  const int col = col0 + c;
+                  float g = 0.f, xh = 0.f;
+                  if (row_ok && col < p.N) {
+                    const float pre = fmaf(__ldg(p.r_scale + col), rv[c], __ldg(p.r_shift + col));
+                    g = round_bf16(v[c] * act_bwd(pre, p.r_act));
+                    xh = (rv[c] - __ldg(p.r_mean + col)) * __ldg(p.r_rstd + col);
+                  }
+                  v[c] = g;
+                  s1[c] = g;
+                  s2[c] = g * xh;
+                }
+              } else {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                  v[c] = round_bf16(v[c] + rv[c]);
+                  s1[c] = 0.f;
+                  s2[c] = 0.f;
+                }
+              }
+            }
+            // ---- store
+            if (row_ok) {
+              if (p.y_is_f32) {
+                float* yp = reinterpret_cast<float*>(p.y) + row * p.ldy + col0;
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                  if (col0 + g * 4 < p.N)
+                    *reinterpret_cast<float4*>(yp + g * 4) =
+                        make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+              } else {
+                __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + row * p.ldy + col0;
+#pragma unroll
+                for (int g = 0; g < 2; ++g)
+                  if (col0 + g * 8 < p.N)
+                    stg_v4(yp + g * 8,
+                           make_uint4(pack_bf16(v[8 * g], v[8 * g + 1]),
+                                      pack_bf16(v[8 * g + 2], v[8 * g + 3]),
+                                      pack_bf16(v[8 * g + 4], v[8 * g + 5]),
+                                      pack_bf16(v[8 * g + 6], v[8 * g + 7])));
+              }
+            }
+            // ---- per-column partial sums over this warp's 32 rows
+            if (want_stats) {
+              const float t1 = warp_colsum16(s1, lane);
+              const float t2 = warp_colsum16(s2, lane);
+              if ((lane & 1) == 0) {
+                stat_warp[(q * 2 + 0) * kMaxBN + j * 16 + (lane >> 1)] = t1;
+                stat_warp[(q * 2 + 1) * kMaxBN + j * 16 + (lane >> 1)] = t2;
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&tempty[buf]);
+        if (want_stats) {
+          named_bar_sync(1, 128);
+          if (et < p.block_n) {
+            const int gc = (nt - nt_begin) * p.block_n + et;
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+              a0 += stat_warp[(w * 2 + 0) * kMaxBN + et];
+              a1 += stat_warp[(w * 2 + 1) * kMaxBN + et];
+            }
+            stat_acc[gc] += a0;
+            stat_acc[kMaxGroupCols + gc] += a1;
+          }
+          named_bar_sync(1, 128);
+        }
+      }
+    if (want_stats) {
+      const int gcols = (nt_end - nt_begin) * p.block_n;
+      for (int c = et; c < gcols; c += 128) {
+        const int col = nt_begin * p.block_n + c;
+        if (col < p.N) {
+          p.stats_part[(static_cast<long long>(blockIdx.x) * 2 + 0) * p.N + col] = stat_acc[c];
+          p.stats_part[(static_cast<long long>(blockIdx.x) * 2 + 1) * p.N + col] =
+              stat_acc[kMaxGroupCols + c];
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight gradient
+// ------------------------------------------------------------------------------------------------
+constexpr int kWgBox = 64 * 64 * 2;          // one TMA box: 64 rows x 64 channels bf16 = 8 KiB
+constexpr int kWgMaxQN = 256;
+constexpr int kWgTmemCols = 256;
+
+struct WgradDev {
+  CUtensorMap tm_p1, tm_p2, tm_q;
+  int Mrows, Cbig, Csmall;
+  int qt;                 // small-side tile width (UMMA N), multiple of 16
+  int qboxes;             // ceil(qt / 64)
+  int stages;
+  int p_mode, p_act;
+  const float *a1, *a2, *a3;
+  float* partials;
+  int kblocks_total, kblocks_per_split;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+pw_wgrad_kernel(const __grid_constant__ WgradDev p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = p.stages;
+  const int p_bytes = (p.p_mode == 2) ? 4 * kWgBox : 2 * kWgBox;
+  const int stage_bytes = p_bytes + 4 * kWgBox;
+  uint8_t* aux = smem + S * stage_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(aux);
+  uint64_t* xf = full + 8;
+  uint64_t* empty = xf + 8;
+  uint64_t* tfull = empty + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 2);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tm_p1);
+    tma_prefetch_desc(&p.tm_q);
+    if (p.p_mode == 2) tma_prefetch_desc(&p.tm_p2);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < S; ++s) {
+        mbar_init(&full[s], 1);
+        mbar_init(&xf[s], 128);
+        mbar_init(&empty[s], 1);
+      }
+      mbar_init(&tfull[0], 1);
+      mbar_fence_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, kWgTmemCols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int bb = blockIdx.x;                 // 128-channel block of the big side
+  const int split = blockIdx.y;
+  const int st = blockIdx.z;                 // tile of the small side
+  const int kb_begin = split * p.kblocks_per_split;
+  const int kb_end = min(p.kblocks_total, kb_begin + p.kblocks_per_split);
+  const int nkb = kb_end - kb_begin;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t tx = static_cast<uint32_t>(p_bytes + p.qboxes * kWgBox);
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % S;
+        const uint32_t ph = (i / S) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_expect_tx(&full[s], tx);
+        uint8_t* sp = smem + s * stage_bytes;
+        const int row = (kb_begin + i) * 64;
+        tma_load_2d(sp, &p.tm_p1, &full[s], bb * 128, row);
+        tma_load_2d(sp + kWgBox, &p.tm_p1, &full[s], bb * 128 + 64, row);
+        if (p.p_mode == 2) {
+          tma_load_2d(sp + 2 * kWgBox, &p.tm_p2, &full[s], bb * 128, row);
+          tma_load_2d(sp + 3 * kWgBox, &p.tm_p2, &full[s], bb * 128 + 64, row);
+        }
+        for (int b = 0; b < p.qboxes; ++b)
+          tma_load_2d(sp + p_bytes + b * kWgBox, &p.tm_q, &full[s], st * p.qt + b * 64, row);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, p.qt, 1, 1);
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % S;
+        const uint32_t ph = (i / S) & 1;
+        mbar_wait(&full[s], ph);
+        if (p.p_mode != 0) mbar_wait(&xf[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
+        const uint32_t b_addr = a_addr + p_bytes;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)      // 16 pixel rows per MMA: 16 x 128 B = 2048 B
+          umma_bf16(tmem_base, umma_desc_sw128(a_addr + k * 2048, kWgBox, 1024),
+                    umma_desc_sw128(b_addr + k * 2048, kWgBox, 1024), idesc,
+                    (i > 0 || k > 0) ? 1u : 0u);
+        umma_commit(&empty[s]);
+        if (i == nkb - 1) umma_commit(&tfull[0]);
+      }
+    }
+  } else if (warp < 6) {
+    if (p.p_mode != 0) {
+      const int t = threadIdx.x - 64;
+      const int cp = t & 7, r0 = t >> 3;
+      const int cl = cp ^ (r0 & 7);
+      float c1[2][8], c2[2][8], c3[2][8];
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int ch = bb * 128 + b * 64 + cl * 8;
+        load_coef8(p.a1, ch, p.Cbig, c1[b], 0.f);
+        load_coef8(p.a3, ch, p.Cbig, c3[b], 0.f);
+        load_coef8(p.p_mode == 2 ? p.a2 : nullptr, ch, p.Cbig, c2[b], 0.f);
+      }
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % S;
+        const uint32_t ph = (i / S) & 1;
+        mbar_wait(&full[s], ph);
+        uint8_t* a = smem + s * stage_bytes + r0 * 128 + cp * 16;
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4* ptr = reinterpret_cast<uint4*>(a + b * kWgBox + j * 16 * 128);
+            const uint4 v = *ptr;
+            uint4 w = make_uint4(0, 0, 0, 0);
+            if (p.p_mode == 2)
+              w = *reinterpret_cast<const uint4*>(a + (b + 2) * kWgBox + j * 16 * 128);
+            *ptr = transform_chunk(v, w, p.p_mode, p.p_act, c1[b], c2[b], c3[b]);
+          }
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&xf[s]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int cb = bb * 128 + q * 32 + lane;
+    mbar_wait(&tfull[0], 0);
+    tc_fence_after();
+    const int nchunks = p.qt / 16;
+    for (int j = 0; j < nchunks; ++j) {
+      float v[16];
+      tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + j * 16, v);
+      const int col0 = st * p.qt + j * 16;
+      if (cb < p.Cbig) {
+        float* dst = p.partials + (static_cast<long long>(split) * p.Cbig + cb) * p.Csmall + col0;
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          if (col0 + g * 4 < p.Csmall)
+            *reinterpret_cast<float4*>(dst + g * 4) =
+                make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kWgTmemCols);
+  }
+}
+
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partials, int splits, int Cbig,
+                                    int Csmall, float* __restrict__ dst, long long sb,
+                                    long long ss) {
+  const long long n = static_cast<long long>(Cbig) * Csmall;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += partials[s * n + i];
+    const long long cb = i / Csmall, cs = i % Csmall;
+    dst[cb * sb + cs * ss] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct GemmPlan {
+  int block_n, n_tiles, m_tiles, groups, tiles_per_group, grid_x;
+};
+
+static GemmPlan plan_gemm(int M, int N) {
+  GemmPlan g;
+  const int sms = sm_count();
+  const int nt0 = (N + kMaxBN - 1) / kMaxBN;
+  g.block_n = (((N + nt0 - 1) / nt0) + 15) / 16 * 16;
+  g.n_tiles = (N + g.block_n - 1) / g.block_n;
+  g.m_tiles = (M + kBM - 1) / kBM;
+  const int max_tpg = kMaxGroupCols / g.block_n;
+  int groups = (g.n_tiles + max_tpg - 1) / max_tpg;
+  if (g.m_tiles < sms) {
+    int want = sms / g.m_tiles;
+    if (want > g.n_tiles) want = g.n_tiles;
+    if (want > groups) groups = want;
+  }
+  g.tiles_per_group = (g.n_tiles + groups - 1) / groups;
+  g.groups = (g.n_tiles + g.tiles_per_group - 1) / g.tiles_per_group;
+  int gx = sms / g.groups;
+  if (gx < 1) gx = 1;
+  if (gx > g.m_tiles) gx = g.m_tiles;
+  g.grid_x = gx;
+  return g;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace an
+
+using namespace an;
+
+extern "C" int an_pw_gemm_stats_rows(int M, int N) { return plan_gemm(M, N).grid_x; }
+
+extern "C" int an_pw_gemm(const an_pw_gemm_args* a, void* stream) {
+  AN_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, "an_pw_gemm: empty problem %d %d %d", a->M, a->N, a->K);
+  AN_REQUIRE(a->K % 8 == 0 && a->N % 8 == 0, "an_pw_gemm: K=%d and N=%d must be multiples of 8", a->K, a->N);
+  AN_REQUIRE(a->ldx1 % 8 == 0 && a->ldw % 8 == 0 && a->ldy % 8 == 0, "an_pw_gemm: pitches must be multiples of 8");
+  AN_REQUIRE(aligned16(a->x1) && aligned16(a->w) && aligned16(a->y), "an_pw_gemm: pointers must be 16-byte aligned");
+  AN_REQUIRE(a->a_mode >= 0 && a->a_mode <= 2 && a->epi_mode >= 0 && a->epi_mode <= 2, "an_pw_gemm: bad mode");
+  if (a->a_mode != 0) AN_REQUIRE(a->a1 && a->a3, "an_pw_gemm: a_mode %d needs a1/a3", a->a_mode);
+  if (a->a_mode == 2) AN_REQUIRE(a->x2 && a->a2 && a->ldx2 % 8 == 0 && aligned16(a->x2), "an_pw_gemm: a_mode 2 needs x2/a2");
+  if (a->epi_mode == 1)
+    AN_REQUIRE(a->r && a->r_scale && a->r_shift && a->r_mean && a->r_rstd && a->ldr % 8 == 0 && aligned16(a->r),
+               "an_pw_gemm: epi_mode 1 needs r and its BN vectors");
+  if (a->epi_mode == 2 && a->r) AN_REQUIRE(a->ldr % 8 == 0 && aligned16(a->r), "an_pw_gemm: bad residual");
+  AN_REQUIRE(!(a->y_is_f32 && a->epi_mode != 0), "an_pw_gemm: f32 output only with epi_mode 0");
+
+  const GemmPlan g = plan_gemm(a->M, a->N);
+  GemmDev d;
+  memset(&d, 0, sizeof(d));
+  if (int e = make_tmap_bf16_2d(&d.tm_x1, a->x1, a->K, a->M, a->ldx1, kBK, kBM)) return e;
+  if (a->a_mode == 2) {
+    if (int e = make_tmap_bf16_2d(&d.tm_x2, a->x2, a->K, a->M, a->ldx2, kBK, kBM)) return e;
+  }
+  if (int e = make_tmap_bf16_2d(&d.tm_w, a->w, a->K, a->N, a->ldw, kBK, g.block_n)) return e;
+  d.M = a->M; d.N = a->N; d.K = a->K;
+  d.block_n = g.block_n; d.m_tiles = g.m_tiles; d.n_tiles = g.n_tiles;
+  d.tiles_per_group = g.tiles_per_group;
+  d.stages = (a->a_mode == 2) ? 3 : 4;
+  d.a_mode = a->a_mode; d.a_act = a->a_act; d.a1 = a->a1; d.a2 = a->a2; d.a3 = a->a3;
+  d.epi_mode = a->epi_mode; d.y = a->y; d.ldy = a->ldy; d.y_is_f32 = a->y_is_f32;
+  d.bias = a->bias; d.stats_part = a->stats_part;
+  d.r = reinterpret_cast<const __nv_bfloat16*>(a->r); d.ldr = a->ldr;
+  d.r_scale = a->r_scale; d.r_shift = a->r_shift; d.r_mean = a->r_mean; d.r_rstd = a->r_rstd;
+  d.r_act = a->r_act;
+
+  const int a_bytes = (a->a_mode == 2) ? 2 * kTileA : kTileA;
+  const int smem = d.stages * (a_bytes + kTileB) + kAuxBytes + 1024;
+  static int configured = 0;
+  if (configured < smem) {
+    AN_CHECK_CUDA(cudaFuncSetAttribute(pw_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = 200 * 1024;
+  }
+  dim3 grid(g.grid_x, g.groups, 1);
+  pw_gemm_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(d);
+  AN_CHECK_LAUNCH();
+  return 0;
+}
+
+namespace an {
+struct WgradPlan {
+  int big_blocks, qt, qboxes, small_tiles, kblocks_total, kblocks_per_split, splits;
+};
+static WgradPlan plan_wgrad(int Mrows, int Cbig, int Csmall) {
+  WgradPlan w;
+  const int sms = sm_count();
+  w.big_blocks = (Cbig + 127) / 128;
+  const int st0 = (Csmall + kWgMaxQN - 1) / kWgMaxQN;
+  w.qt = (((Csmall + st0 - 1) / st0) + 15) / 16 * 16;
+  w.small_tiles = (Csmall + w.qt - 1) / w.qt;
+  w.qboxes = (w.qt + 63) / 64;
+  w.kblocks_total = (Mrows + 63) / 64;
+  int want = (2 * sms) / (w.big_blocks * w.small_tiles);
+  if (want < 1) want = 1;
+  // keep each split at >= 8 k-blocks (512 pixel rows) so the TMEM drain is amortised
+  int max_splits = (w.kblocks_total + 7) / 8;
+  if (max_splits < 1) max_splits = 1;
+  if (want > max_splits) want = max_splits;
+  w.kblocks_per_split = (w.kblocks_total + want - 1) / want;
+  w.splits = (w.kblocks_total + w.kblocks_per_split - 1) / w.kblocks_per_split;
+  return w;
+}
+}  // namespace an
+
+extern "C" int an_pw_wgrad_splits(int Mrows, int Cbig, int Csmall) {
+  return plan_wgrad(Mrows, Cbig, Csmall).splits;
+}
+
+extern "C" int an_pw_wgrad(const an_pw_wgrad_args* a, void* stream) {
+  AN_REQUIRE(a->Mrows > 0 && a->Cbig > 0 && a->Csmall > 0, "an_pw_wgrad: empty problem");
+  AN_REQUIRE(a->Cbig % 8 == 0 && a->Csmall % 8 == 0, "an_pw_wgrad: channel counts must be multiples of 8");
+  AN_REQUIRE(a->ldp1 % 8 == 0 && a->ldq % 8 == 0 && aligned16(a->p1) && aligned16(a->q), "an_pw_wgrad: bad operand layout");
+  AN_REQUIRE(a->p_mode >= 0 && a->p_mode <= 2, "an_pw_wgrad: bad p_mode");
+  if (a->p_mode != 0) AN_REQUIRE(a->a1 && a->a3, "an_pw_wgrad: p_mode needs a1/a3");
+  if (a->p_mode == 2) AN_REQUIRE(a->p2 && a->a2 && a->ldp2 % 8 == 0 && aligned16(a->p2), "an_pw_wgrad: p_mode 2 needs p2/a2");
+  const WgradPlan w = plan_wgrad(a->Mrows, a->Cbig, a->Csmall);
+  AN_REQUIRE(a->splits == w.splits, "an_pw_wgrad: splits %d != planned %d", a->splits, w.splits);
+  AN_REQUIRE(a->partials != nullptr && aligned16(a->partials), "an_pw_wgrad: partials buffer missing");
+
+  WgradDev d;
+  memset(&d, 0, sizeof(d));
+  if (int e = make_tmap_bf16_2d(&d.tm_p1, a->p1, a->Cbig, a->Mrows, a->ldp1, 64, 64)) return e;
+  if (a->p_mode == 2) {
+    if (int e = make_tmap_bf16_2d(&d.tm_p2, a->p2, a->Cbig, a->Mrows, a->ldp2, 64, 64)) return e;
+  }
+  if (int e = make_tmap_bf16_2d(&d.tm_q, a->q, a->Csmall, a->Mrows, a->ldq, 64, 64)) return e;
+  d.Mrows = a->Mrows; d.Cbig = a->Cbig; d.Csmall = a->Csmall;
+  d.qt = w.qt; d.qboxes = w.qboxes;
+  d.stages = 3;
+  d.p_mode = a->p_mode; d.p_act = a->p_act; d.a1 = a->a1; d.a2 = a->a2; d.a3 = a->a3;
+  d.partials = a->partials;
+  d.kblocks_total = w.kblocks_total; d.kblocks_per_split = w.kblocks_per_split;
+  const int p_bytes = (a->p_mode == 2) ? 4 * kWgBox : 2 * kWgBox;
+  const int smem = d.stages * (p_bytes + 4 * kWgBox) + 256 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    AN_CHECK_CUDA(cudaFuncSetAttribute(pw_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = true;
+  }
+  dim3 grid(w.big_blocks, w.splits, w.small_tiles);
+  pw_wgrad_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(d);
+  AN_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int an_wgrad_reduce(const float* partials, int splits, int Cbig, int Csmall, float* dst,
+                               long long dst_sb, long long dst_ss, void* stream) {
+  AN_REQUIRE(partials && dst && splits > 0, "an_wgrad_reduce: bad arguments");
+  const long long n = static_cast<long long>(Cbig) * Csmall;
+  int blocks = static_cast<int>((n + 255) / 256);
+  if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
+  wgrad_reduce_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(partials, splits, Cbig, Csmall, dst, dst_sb, dst_ss);
+  AN_CHECK_LAUNCH();
+  return 0;
+}
