@@ -38,6 +38,26 @@ class PwWgradArgs(ctypes.Structure):
     ]
 
 
+class DwFwdArgs(ctypes.Structure):
+    _fields_ = [
+        ("x", c_vp), ("ldx", c_ll), ("y", c_vp), ("ldy", c_ll), ("w", c_fp), ("scale", c_fp),
+        ("shift", c_fp), ("stats_part", c_fp), ("act", c_int),
+        ("B", c_int), ("H", c_int), ("W", c_int), ("C", c_int), ("k", c_int), ("stride", c_int),
+    ]
+
+
+class DwBwdArgs(ctypes.Structure):
+    _fields_ = [
+        ("g", c_vp), ("ldg", c_ll), ("draw", c_vp), ("ldd", c_ll), ("eraw", c_vp), ("lde", c_ll),
+        ("ge", c_vp), ("ldge", c_ll), ("w", c_fp), ("ca", c_fp), ("cb", c_fp), ("cc", c_fp),
+        ("e_scale", c_fp), ("e_shift", c_fp), ("e_mean", c_fp), ("e_rstd", c_fp),
+        ("stats_part", c_fp), ("act", c_int),
+        ("B", c_int), ("H", c_int), ("W", c_int), ("C", c_int), ("k", c_int), ("stride", c_int),
+    ]
+
+
+c_f, c_d, c_ull = ctypes.c_float, ctypes.c_double, ctypes.c_ulonglong
+
 # name -> (restype, argtypes); must list every symbol of include/atomnas_b200.h
 SIGNATURES = {
     "an_last_error": (ctypes.c_char_p, []),
@@ -48,6 +68,39 @@ SIGNATURES = {
     "an_pw_wgrad_splits": (c_int, [c_int, c_int, c_int]),
     "an_pw_wgrad": (c_int, [ctypes.POINTER(PwWgradArgs), c_vp]),
     "an_wgrad_reduce": (c_int, [c_fp, c_int, c_int, c_int, c_fp, c_ll, c_ll, c_vp]),
+    "an_dw_fwd": (c_int, [ctypes.POINTER(DwFwdArgs), c_vp]),
+    "an_dw_fwd_stats_rows": (c_int, [c_int] * 6),
+    "an_dw_bwd_data": (c_int, [ctypes.POINTER(DwBwdArgs), c_vp]),
+    "an_dw_bwd_data_stats_rows": (c_int, [c_int] * 6),
+    "an_dw_bwd_weight": (c_int, [ctypes.POINTER(DwBwdArgs), c_fp, c_fp, c_vp]),
+    "an_dw_bwd_weight_rows": (c_int, [c_int] * 6),
+    "an_bn_finalize": (c_int, [c_fp, c_int, c_int, c_d, c_fp, c_fp, c_fp, c_fp, c_f, c_f, c_fp,
+                               c_fp, c_fp, c_fp, c_vp]),
+    "an_bn_bwd_finalize": (c_int, [c_fp, c_int, c_int, c_d, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp,
+                                   c_fp, c_fp, c_vp]),
+    "an_affine_act": (c_int, [c_vp, c_ll, c_vp, c_ll, c_fp, c_fp, c_fp, c_int, c_vp, c_ll, c_ll,
+                              c_int, c_vp]),
+    "an_col_reduce_rows": (c_int, [c_ll, c_int]),
+    "an_col_reduce": (c_int, [c_vp, c_ll, c_vp, c_ll, c_fp, c_fp, c_ll, c_int, c_fp, c_vp]),
+    "an_stem_fwd": (c_int, [c_fp, c_fp, c_vp, c_ll, c_fp, c_int, c_int, c_int, c_int, c_vp]),
+    "an_stem_fwd_stats_rows": (c_int, [c_int, c_int, c_int]),
+    "an_stem_wgrad": (c_int, [c_fp, c_vp, c_ll, c_vp, c_ll, c_fp, c_fp, c_fp, c_fp, c_fp, c_int,
+                              c_int, c_int, c_int, c_vp]),
+    "an_stem_wgrad_rows": (c_int, [c_int, c_int, c_int]),
+    "an_pool_fwd": (c_int, [c_vp, c_ll, c_fp, c_fp, c_int, c_vp, c_ll, c_int, c_int, c_int, c_f,
+                            c_ull, c_vp]),
+    "an_pool_bwd": (c_int, [c_vp, c_ll, c_vp, c_ll, c_fp, c_fp, c_fp, c_fp, c_int, c_vp, c_ll,
+                            c_fp, c_int, c_int, c_int, c_f, c_ull, c_vp]),
+    "an_pool_bwd_stats_rows": (c_int, [c_int]),
+    "an_ce_loss": (c_int, [c_fp, c_ll, c_vp, c_int, c_int, c_f, c_f, c_fp, c_vp, c_ll, c_int,
+                           c_vp]),
+    "an_f32_to_bf16": (c_int, [c_fp, c_ll, c_vp, c_ll, c_ll, c_int, c_int, c_vp]),
+    "an_rmsprop_ema_step": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_ll, c_f, c_f, c_f,
+                                    c_f, c_int, c_f, c_f, c_f, c_f, c_vp]),
+    "an_ema_update": (c_int, [c_fp, c_fp, c_ll, c_f, c_vp]),
+    "an_reg_losses": (c_int, [c_fp, c_fp, c_fp, c_ll, c_fp, c_vp]),
+    "an_refresh_weights": (c_int, [c_vp, c_int, c_ll, c_fp, c_vp, c_fp, c_vp]),
+    "an_gather_rows": (c_int, [c_fp, c_vp, c_ll, c_ll, c_fp, c_vp]),
 }
 
 _lib = None

@@ -1,0 +1,235 @@
+// BatchNorm2d (training mode) split into tiny finalize kernels + per-channel affine passes.
+//
+// Reference semantics: nn.BatchNorm2d at models/mobilenet_base.py:142 and :342 (momentum / eps
+// from the YAML, apps/slimming/shrink/atomnas_c.yml:27-28): normalise with the biased batch
+// variance, store the unbiased one in running_var, running = (1-m)*running + m*batch;
+// momentum=None (BN calibration, utils/common.py:214-226) is passed by the host as m = 1/nbt.
+// The per-channel sums come from the producing conv kernel's epilogue; these kernels only
+// combine the partials (fixed order, fp64 accumulation) and emit the scale/shift vectors the
+// consumer kernels apply on load.
+#include "common.cuh"
+#include "../../include/atomnas_b200.h"
+
+namespace an {
+
+__global__ void bn_finalize_kernel(const float* __restrict__ part, int rows, int C, double count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* running_mean, float* running_var, float momentum,
+                                   float eps, float* mean_out, float* rstd_out, float* scale_out,
+                                   float* shift_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (int r = 0; r < rows; ++r) {
+    s1 += static_cast<double>(part[(static_cast<long long>(r) * 2 + 0) * C + c]);
+    s2 += static_cast<double>(part[(static_cast<long long>(r) * 2 + 1) * C + c]);
+  }
+  const double mean = s1 / count;
+  double var = s2 / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  const float fm = static_cast<float>(mean);
+  mean_out[c] = fm;
+  rstd_out[c] = rstd;
+  const float sc = g * rstd;
+  scale_out[c] = sc;
+  shift_out[c] = b - fm * sc;
+  if (running_mean != nullptr) {
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * fm;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
+  }
+}
+
+// dgamma = sum g*xhat, dbeta = sum g, and the coefficients of
+//   dx = ca*g + cb*x + cc   ( = gamma*rstd*(g - mean(g) - xhat*mean(g*xhat)) )
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int rows, int C,
+                                       double count, const float* __restrict__ gamma,
+                                       const float* __restrict__ mean,
+                                       const float* __restrict__ rstd, float* dgamma, float* dbeta,
+                                       float* ca, float* cb, float* cc) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (int r = 0; r < rows; ++r) {
+    s1 += static_cast<double>(part[(static_cast<long long>(r) * 2 + 0) * C + c]);
+    s2 += static_cast<double>(part[(static_cast<long long>(r) * 2 + 1) * C + c]);
+  }
+  if (dbeta) dbeta[c] = static_cast<float>(s1);
+  if (dgamma) dgamma[c] = static_cast<float>(s2);
+  const float g = gamma ? gamma[c] : 1.f;
+  const float a = g * rstd[c];
+  const float b = -a * rstd[c] * static_cast<float>(s2 / count);
+  ca[c] = a;
+  cb[c] = b;
+  cc[c] = -a * static_cast<float>(s1 / count) - b * mean[c];
+}
+
+// out = act(a1[c]*x1 + a2[c]*x2 + a3[c]); a1/a2 default 1, a3 default 0, x2 optional.
+__global__ void affine_act_kernel(const __nv_bfloat16* __restrict__ x1, long long ld1,
+                                  const __nv_bfloat16* __restrict__ x2, long long ld2,
+                                  const float* __restrict__ a1, const float* __restrict__ a2,
+                                  const float* __restrict__ a3, int act, __nv_bfloat16* out,
+                                  long long ldo, long long M, int C) {
+  const int ncg = C / 8;
+  const long long total = M * ncg;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / ncg;
+    const int ch = static_cast<int>(i % ncg) * 8;
+    float c1[8], c2[8], c3[8];
+    load_coef8(a1, ch, C, c1, 1.f);
+    load_coef8(a2, ch, C, c2, 1.f);
+    load_coef8(a3, ch, C, c3, 0.f);
+    const uint4 v = ldg_nc_v4(x1 + row * ld1 + ch);
+    uint4 w = make_uint4(0, 0, 0, 0);
+    if (x2 != nullptr) w = ldg_nc_v4(x2 + row * ld2 + ch);
+    const uint32_t vi[4] = {v.x, v.y, v.z, v.w}, wi[4] = {w.x, w.y, w.z, w.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float lo = fmaf(c1[2 * e], bf16_lo(vi[e]), c3[2 * e]);
+      float hi = fmaf(c1[2 * e + 1], bf16_hi(vi[e]), c3[2 * e + 1]);
+      if (x2 != nullptr) {
+        lo = fmaf(c2[2 * e], bf16_lo(wi[e]), lo);
+        hi = fmaf(c2[2 * e + 1], bf16_hi(wi[e]), hi);
+      }
+      o[e] = pack_bf16(act_fwd(lo, act), act_fwd(hi, act));
+    }
+    stg_v4(out + row * ldo + ch, make_uint4(o[0], o[1], o[2], o[3]));
+  }
+}
+
+// Per-channel partials of sum(g) and sum(g*xhat), xhat = (x-mean)*rstd, over a [M, C] matrix.
+// (x == nullptr: sum(g) and sum(g*g) -- plain column statistics.)
+constexpr int kRedThreads = 256;
+__global__ void col_reduce_kernel(const __nv_bfloat16* __restrict__ g, long long ldg,
+                                  const __nv_bfloat16* __restrict__ x, long long ldx,
+                                  const float* __restrict__ mean, const float* __restrict__ rstd,
+                                  long long M, int C, int rows_per_cta, float* part) {
+  __shared__ float red[kRedThreads * 16];
+  const int ncg = C / 8;
+  const int cgb = min(ncg, 32);                 // channel groups per CTA
+  const int lanes = kRedThreads / cgb;          // row lanes
+  const int lcg = threadIdx.x % cgb, rl = threadIdx.x / cgb;
+  const int cg = blockIdx.y * cgb + lcg;
+  const int ch = cg * 8;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) { s1[c] = 0.f; s2[c] = 0.f; }
+  if (cg < ncg && rl < lanes) {
+    float mu[8], rs[8];
+    load_coef8(mean, ch, C, mu, 0.f);
+    load_coef8(rstd, ch, C, rs, 1.f);
+    const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
+    const long long r1 = min(M, r0 + rows_per_cta);
+    for (long long r = r0 + rl; r < r1; r += lanes) {
+      const uint4 gv = ldg_nc_v4(g + r * ldg + ch);
+      const uint32_t gi[4] = {gv.x, gv.y, gv.z, gv.w};
+      float gf[8];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { gf[2 * e] = bf16_lo(gi[e]); gf[2 * e + 1] = bf16_hi(gi[e]); }
+      if (x != nullptr) {
+        const uint4 xv = ldg_nc_v4(x + r * ldx + ch);
+        const uint32_t xi[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float xl = (bf16_lo(xi[e]) - mu[2 * e]) * rs[2 * e];
+          const float xh = (bf16_hi(xi[e]) - mu[2 * e + 1]) * rs[2 * e + 1];
+          s1[2 * e] += gf[2 * e];
+          s1[2 * e + 1] += gf[2 * e + 1];
+          s2[2 * e] = fmaf(gf[2 * e], xl, s2[2 * e]);
+          s2[2 * e + 1] = fmaf(gf[2 * e + 1], xh, s2[2 * e + 1]);
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { s1[c] += gf[c]; s2[c] = fmaf(gf[c], gf[c], s2[c]); }
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    red[threadIdx.x * 16 + c] = s1[c];
+    red[threadIdx.x * 16 + 8 + c] = s2[c];
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < cgb * 16; o += kRedThreads) {
+    const int l = o / 16, e = o % 16;
+    float a = 0.f;
+    for (int r = 0; r < lanes; ++r) a += red[(r * cgb + l) * 16 + e];
+    const int c = (blockIdx.y * cgb + l) * 8 + (e & 7);
+    if (c < C) part[(static_cast<long long>(blockIdx.x) * 2 + (e >> 3)) * C + c] = a;
+  }
+}
+
+static int col_reduce_rows_per_cta(long long M, int C) {
+  const int ncg = C / 8, cgb = ncg < 32 ? ncg : 32;
+  const int ygrid = (ncg + cgb - 1) / cgb;
+  long long want_ctas = (4LL * sm_count() + ygrid - 1) / ygrid;
+  long long rpc = (M + want_ctas - 1) / want_ctas;
+  if (rpc < 64) rpc = 64;
+  return static_cast<int>(rpc);
+}
+
+}  // namespace an
+
+using namespace an;
+
+extern "C" int an_bn_finalize(const float* stats_part, int rows, int C, double count,
+                              const float* gamma, const float* beta, float* running_mean,
+                              float* running_var, float momentum, float eps, float* mean,
+                              float* rstd, float* scale, float* shift, void* stream) {
+  AN_REQUIRE(stats_part && rows > 0 && C > 0 && mean && rstd && scale && shift, "an_bn_finalize: bad arguments");
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      stats_part, rows, C, count, gamma, beta, running_mean, running_var, momentum, eps, mean, rstd,
+      scale, shift);
+  AN_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int an_bn_bwd_finalize(const float* stats_part, int rows, int C, double count,
+                                  const float* gamma, const float* mean, const float* rstd,
+                                  float* dgamma, float* dbeta, float* ca, float* cb, float* cc,
+                                  void* stream) {
+  AN_REQUIRE(stats_part && rows > 0 && C > 0 && mean && rstd && ca && cb && cc, "an_bn_bwd_finalize: bad arguments");
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      stats_part, rows, C, count, gamma, mean, rstd, dgamma, dbeta, ca, cb, cc);
+  AN_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int an_affine_act(const void* x1, long long ld1, const void* x2, long long ld2,
+                             const float* a1, const float* a2, const float* a3, int act, void* out,
+                             long long ldo, long long M, int C, void* stream) {
+  AN_REQUIRE(x1 && out && M > 0 && C > 0 && C % 8 == 0 && ld1 % 8 == 0 && ldo % 8 == 0 && (x2 == nullptr || ld2 % 8 == 0),
+             "an_affine_act: bad arguments");
+  const long long total = M * (C / 8);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 16LL * sm_count()) blocks = 16LL * sm_count();
+  affine_act_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x1), ld1, reinterpret_cast<const __nv_bfloat16*>(x2), ld2,
+      a1, a2, a3, act, reinterpret_cast<__nv_bfloat16*>(out), ldo, M, C);
+  AN_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int an_col_reduce_rows(long long M, int C) {
+  const int rpc = col_reduce_rows_per_cta(M, C);
+  return static_cast<int>((M + rpc - 1) / rpc);
+}
+
+extern "C" int an_col_reduce(const void* g, long long ldg, const void* x, long long ldx,
+                             const float* mean, const float* rstd, long long M, int C,
+                             float* stats_part, void* stream) {
+  AN_REQUIRE(g && stats_part && M > 0 && C > 0 && C % 8 == 0 && ldg % 8 == 0, "an_col_reduce: bad arguments");
+  if (x) AN_REQUIRE(mean && rstd && ldx % 8 == 0, "an_col_reduce: x needs mean/rstd");
+  const int rpc = col_reduce_rows_per_cta(M, C);
+  const int ncg = C / 8, cgb = ncg < 32 ? ncg : 32;
+  dim3 grid(static_cast<unsigned>((M + rpc - 1) / rpc), (ncg + cgb - 1) / cgb);
+  col_reduce_kernel<<<grid, kRedThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(g), ldg, reinterpret_cast<const __nv_bfloat16*>(x), ldx, mean,
+      rstd, M, C, rpc, stats_part);
+  AN_CHECK_LAUNCH();
+  return 0;
+}

@@ -272,6 +272,20 @@ __device__ __forceinline__ float warp_colsum16(const float* v, int lane) {
   return d;
 }
 
+// 8 consecutive channels of a per-channel coefficient vector (zero beyond `limit`).
+__device__ __forceinline__ void load_coef8(const float* p, int ch, int limit, float* out,
+                                           float fill) {
+  if (p != nullptr && ch < limit) {
+    const float4 lo = __ldg(reinterpret_cast<const float4*>(p + ch));
+    const float4 hi = __ldg(reinterpret_cast<const float4*>(p + ch + 4));
+    out[0] = lo.x; out[1] = lo.y; out[2] = lo.z; out[3] = lo.w;
+    out[4] = hi.x; out[5] = hi.y; out[6] = hi.z; out[7] = hi.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) out[i] = fill;
+  }
+}
+
 __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
   uint4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"

@@ -48,20 +48,6 @@ struct GemmDev {
   int r_act;
 };
 
-// 8 consecutive channels of a per-channel coefficient vector (zero beyond `limit`).
-__device__ __forceinline__ void load_coef8(const float* p, int ch, int limit, float* out,
-                                           float fill) {
-  if (p != nullptr && ch < limit) {
-    const float4 lo = __ldg(reinterpret_cast<const float4*>(p + ch));
-    const float4 hi = __ldg(reinterpret_cast<const float4*>(p + ch + 4));
-    out[0] = lo.x; out[1] = lo.y; out[2] = lo.z; out[3] = lo.w;
-    out[4] = hi.x; out[5] = hi.y; out[6] = hi.z; out[7] = hi.w;
-  } else {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) out[i] = fill;
-  }
-}
-
 // In-place prologue on one 16-byte chunk (8 channels) of a swizzled operand tile.
 __device__ __forceinline__ uint4 transform_chunk(uint4 v, uint4 w, int mode, int act,
                                                  const float* c1, const float* c2,

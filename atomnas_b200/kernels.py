@@ -61,3 +61,166 @@ def pw_wgrad(p1, q, partials, Mrows, Cbig, Csmall, *, ldp1=None, ldq=None, p2=No
 def wgrad_reduce(partials, splits, Cbig, Csmall, dst, sb, ss):
     L.check(L.lib().an_wgrad_reduce(_c(partials), splits, Cbig, Csmall, _c(dst), sb, ss,
                                     L.stream_ptr()), "an_wgrad_reduce")
+
+
+# ------------------------------------------------------------------------------------------------
+# depthwise
+# ------------------------------------------------------------------------------------------------
+def dw_out_hw(H, W, k, stride):
+    p = (k - 1) // 2
+    return (H + 2 * p - k) // stride + 1, (W + 2 * p - k) // stride + 1
+
+
+def dw_fwd_stats_rows(B, C, Ho, Wo, k, stride):
+    return L.lib().an_dw_fwd_stats_rows(B, C, Ho, Wo, k, stride)
+
+
+def dw_fwd(x, y, w, B, H, W, C, k, stride, *, ldx, ldy, scale=None, shift=None, act=0,
+           stats_part=None):
+    a = L.DwFwdArgs()
+    a.x, a.ldx, a.y, a.ldy = _c(x), ldx, _c(y), ldy
+    a.w, a.scale, a.shift, a.stats_part = _c(w), _c(scale), _c(shift), _c(stats_part)
+    a.act = act
+    a.B, a.H, a.W, a.C, a.k, a.stride = B, H, W, C, k, stride
+    L.check(L.lib().an_dw_fwd(a, L.stream_ptr()), "an_dw_fwd")
+
+
+def _dw_bwd_args(g, draw, eraw, ge, w, ca, cb, cc, e_scale, e_shift, e_mean, e_rstd, stats_part,
+                 act, B, H, W, C, k, stride, ldg, ldd, lde, ldge):
+    a = L.DwBwdArgs()
+    a.g, a.ldg, a.draw, a.ldd, a.eraw, a.lde = _c(g), ldg, _c(draw), ldd, _c(eraw), lde
+    a.ge, a.ldge = _c(ge), ldge
+    a.w, a.ca, a.cb, a.cc = _c(w), _c(ca), _c(cb), _c(cc)
+    a.e_scale, a.e_shift, a.e_mean, a.e_rstd = _c(e_scale), _c(e_shift), _c(e_mean), _c(e_rstd)
+    a.stats_part = _c(stats_part)
+    a.act = act
+    a.B, a.H, a.W, a.C, a.k, a.stride = B, H, W, C, k, stride
+    return a
+
+
+def dw_bwd_data_stats_rows(B, C, H, W, k, stride):
+    return L.lib().an_dw_bwd_data_stats_rows(B, C, H, W, k, stride)
+
+
+def dw_bwd_data(g, draw, eraw, ge, w, ca, cb, cc, e_scale, e_shift, e_mean, e_rstd, stats_part, act,
+                B, H, W, C, k, stride, *, ldg, ldd, lde, ldge):
+    a = _dw_bwd_args(g, draw, eraw, ge, w, ca, cb, cc, e_scale, e_shift, e_mean, e_rstd, stats_part,
+                     act, B, H, W, C, k, stride, ldg, ldd, lde, ldge)
+    L.check(L.lib().an_dw_bwd_data(a, L.stream_ptr()), "an_dw_bwd_data")
+
+
+def dw_bwd_weight_rows(B, C, H, W, k, stride):
+    return L.lib().an_dw_bwd_weight_rows(B, C, H, W, k, stride)
+
+
+def dw_bwd_weight(g, draw, eraw, ca, cb, cc, e_scale, e_shift, act, partials, dw, B, H, W, C, k,
+                  stride, *, ldg, ldd, lde):
+    a = _dw_bwd_args(g, draw, eraw, None, None, ca, cb, cc, e_scale, e_shift, None, None, None, act,
+                     B, H, W, C, k, stride, ldg, ldd, lde, 8)
+    L.check(L.lib().an_dw_bwd_weight(a, _c(partials), _c(dw), L.stream_ptr()), "an_dw_bwd_weight")
+
+
+# ------------------------------------------------------------------------------------------------
+# batch norm pieces
+# ------------------------------------------------------------------------------------------------
+def bn_finalize(part, rows, C, count, gamma, beta, rm, rv, momentum, eps, mean, rstd, scale, shift):
+    L.check(L.lib().an_bn_finalize(_c(part), rows, C, float(count), _c(gamma), _c(beta), _c(rm),
+                                   _c(rv), momentum, eps, _c(mean), _c(rstd), _c(scale), _c(shift),
+                                   L.stream_ptr()), "an_bn_finalize")
+
+
+def bn_bwd_finalize(part, rows, C, count, gamma, mean, rstd, dgamma, dbeta, ca, cb, cc):
+    L.check(L.lib().an_bn_bwd_finalize(_c(part), rows, C, float(count), _c(gamma), _c(mean),
+                                       _c(rstd), _c(dgamma), _c(dbeta), _c(ca), _c(cb), _c(cc),
+                                       L.stream_ptr()), "an_bn_bwd_finalize")
+
+
+def affine_act(x1, out, M, C, *, ld1, ldo, x2=None, ld2=0, a1=None, a2=None, a3=None, act=0):
+    L.check(L.lib().an_affine_act(_c(x1), ld1, _c(x2), ld2, _c(a1), _c(a2), _c(a3), act, _c(out),
+                                  ldo, M, C, L.stream_ptr()), "an_affine_act")
+
+
+def col_reduce_rows(M, C):
+    return L.lib().an_col_reduce_rows(M, C)
+
+
+def col_reduce(g, part, M, C, *, ldg, x=None, ldx=0, mean=None, rstd=None):
+    L.check(L.lib().an_col_reduce(_c(g), ldg, _c(x), ldx, _c(mean), _c(rstd), M, C, _c(part),
+                                  L.stream_ptr()), "an_col_reduce")
+
+
+# ------------------------------------------------------------------------------------------------
+# stem / head / loss
+# ------------------------------------------------------------------------------------------------
+def stem_fwd_stats_rows(B, Ho, Wo):
+    return L.lib().an_stem_fwd_stats_rows(B, Ho, Wo)
+
+
+def stem_fwd(x, w, y, part, B, H, W, C, *, ldy):
+    L.check(L.lib().an_stem_fwd(_c(x), _c(w), _c(y), ldy, _c(part), B, H, W, C, L.stream_ptr()),
+            "an_stem_fwd")
+
+
+def stem_wgrad_rows(B, Ho, Wo):
+    return L.lib().an_stem_wgrad_rows(B, Ho, Wo)
+
+
+def stem_wgrad(x, g, sraw, ca, cb, cc, partials, dw, B, H, W, C, *, ldg, lds):
+    L.check(L.lib().an_stem_wgrad(_c(x), _c(g), ldg, _c(sraw), lds, _c(ca), _c(cb), _c(cc),
+                                  _c(partials), _c(dw), B, H, W, C, L.stream_ptr()), "an_stem_wgrad")
+
+
+def pool_fwd(h, scale, shift, act, pooled, B, HW, C, *, ldh, ldp, drop_p=0.0, seed=0):
+    L.check(L.lib().an_pool_fwd(_c(h), ldh, _c(scale), _c(shift), act, _c(pooled), ldp, B, HW, C,
+                                drop_p, seed, L.stream_ptr()), "an_pool_fwd")
+
+
+def pool_bwd_stats_rows(B):
+    return L.lib().an_pool_bwd_stats_rows(B)
+
+
+def pool_bwd(dpooled, h, scale, shift, mean, rstd, act, gh, part, B, HW, C, *, ldd, ldh, ldg,
+             drop_p=0.0, seed=0):
+    L.check(L.lib().an_pool_bwd(_c(dpooled), ldd, _c(h), ldh, _c(scale), _c(shift), _c(mean),
+                                _c(rstd), act, _c(gh), ldg, _c(part), B, HW, C, drop_p, seed,
+                                L.stream_ptr()), "an_pool_bwd")
+
+
+def ce_loss(logits, labels, B, NC, eps, grad_scale, loss, dlogits, *, ldl, ldd, nd_pad):
+    L.check(L.lib().an_ce_loss(_c(logits), ldl, _c(labels), B, NC, eps, grad_scale, _c(loss),
+                               _c(dlogits), ldd, nd_pad, L.stream_ptr()), "an_ce_loss")
+
+
+def f32_to_bf16(src, dst, rows, cols, cols_pad, *, lds, ldd):
+    L.check(L.lib().an_f32_to_bf16(_c(src), lds, _c(dst), ldd, rows, cols, cols_pad,
+                                   L.stream_ptr()), "an_f32_to_bf16")
+
+
+# ------------------------------------------------------------------------------------------------
+# optimizer / weights
+# ------------------------------------------------------------------------------------------------
+def rmsprop_ema_step(p, g, sq, buf, ema, wd_flag, l1_pen, n, lr, alpha, momentum, eps,
+                     eps_inside_sqrt, grad_scale, weight_decay, rho, ema_decay):
+    L.check(L.lib().an_rmsprop_ema_step(_c(p), _c(g), _c(sq), _c(buf), _c(ema), _c(wd_flag),
+                                        _c(l1_pen), n, lr, alpha, momentum, eps,
+                                        1 if eps_inside_sqrt else 0, grad_scale, weight_decay, rho,
+                                        ema_decay, L.stream_ptr()), "an_rmsprop_ema_step")
+
+
+def ema_update(ema, x, n, decay):
+    L.check(L.lib().an_ema_update(_c(ema), _c(x), n, decay, L.stream_ptr()), "an_ema_update")
+
+
+def reg_losses(p, wd_flag, l1_pen, n, part):
+    L.check(L.lib().an_reg_losses(_c(p), _c(wd_flag), _c(l1_pen), n, _c(part), L.stream_ptr()),
+            "an_reg_losses")
+
+
+def refresh_weights(table, n_entries, total_tiles, src, dst16, dst32):
+    L.check(L.lib().an_refresh_weights(_c(table), n_entries, total_tiles, _c(src), _c(dst16),
+                                       _c(dst32), L.stream_ptr()), "an_refresh_weights")
+
+
+def gather_rows(src, idx, n_out, inner, dst):
+    L.check(L.lib().an_gather_rows(_c(src), _c(idx), n_out, inner, _c(dst), L.stream_ptr()),
+            "an_gather_rows")

@@ -93,6 +93,119 @@ int an_pw_wgrad(const an_pw_wgrad_args* args, void* stream);
 int an_wgrad_reduce(const float* partials, int splits, int Cbig, int Csmall, float* dst,
                     long long dst_sb, long long dst_ss, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Depthwise k x k convolution (k = 3, 5, 7; stride 1, 2; pad (k-1)/2), NHWC bf16, CUDA cores.
+ * Replaces ConvBNReLU(h, h, k, stride, groups=h) models/mobilenet_base.py:330-336 (pad :133)
+ * and its autograd backward.  Pointers are pre-offset to the branch's first channel; C is the
+ * branch width, ld* the full row pitch of the (branch-fused) tensor.
+ *   forward : y = dwconv(act(scale*x + shift)) (scale == NULL: x used as is), BN partials of y
+ *   bwd_data: dd = ca*g + cb*draw + cc; du = dwconv^T(dd);
+ *             ge = du * act'(e_scale*eraw + e_shift); partials sum(ge), sum(ge*xhat_e)
+ *   bwd_weight: dW[c][kr][kc] = sum dd * act(e_scale*eraw + e_shift) (master layout [C,1,k,k])
+ * w is tap-major fp32 [k*k][C] (written by an_refresh_weights).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  const void* x; long long ldx;
+  void* y; long long ldy;
+  const float* w;
+  const float* scale; const float* shift;
+  float* stats_part;
+  int act;
+  int B, H, W, C, k, stride;
+} an_dw_fwd_args;
+
+typedef struct {
+  const void* g; long long ldg;         /* bf16 [B,Ho,Wo,*] grad wrt this layer's BN output */
+  const void* draw; long long ldd;      /* bf16 raw conv output saved by forward */
+  const void* eraw; long long lde;      /* bf16 [B,H,W,*] raw input (producer conv output) */
+  void* ge; long long ldge;             /* out (bwd_data) */
+  const float* w;
+  const float* ca; const float* cb; const float* cc;
+  const float* e_scale; const float* e_shift; const float* e_mean; const float* e_rstd;
+  float* stats_part;
+  int act;
+  int B, H, W, C, k, stride;
+} an_dw_bwd_args;
+
+int an_dw_fwd(const an_dw_fwd_args* args, void* stream);
+int an_dw_fwd_stats_rows(int B, int C, int Ho, int Wo, int k, int stride);
+int an_dw_bwd_data(const an_dw_bwd_args* args, void* stream);
+int an_dw_bwd_data_stats_rows(int B, int C, int H, int W, int k, int stride);
+int an_dw_bwd_weight(const an_dw_bwd_args* args, float* partials, float* dw, void* stream);
+int an_dw_bwd_weight_rows(int B, int C, int H, int W, int k, int stride);
+
+/* ------------------------------------------------------------------------------------------
+ * BatchNorm2d (training mode) pieces -- nn.BatchNorm2d at models/mobilenet_base.py:142, :342.
+ * The conv kernels produce per-CTA partials [rows][2][C]; these combine them.
+ *   an_bn_finalize     : mean/rstd (saved for backward), scale = gamma*rstd, shift = beta-mean*scale,
+ *                        running stats update (momentum m; calibration passes m = 1/nbt)
+ *   an_bn_bwd_finalize : dgamma = sum g*xhat, dbeta = sum g, and (ca,cb,cc) with dx = ca*g+cb*x+cc
+ *   an_affine_act      : out = act(a1*x1 + a2*x2 + a3) (NULL coefficient = 1, 1, 0; x2 optional):
+ *                        pw_bn apply + residual (:379-381), BN-backward apply
+ *   an_col_reduce      : partials of sum g, sum g*xhat over a [M,C] matrix (pw_bn backward)
+ * ------------------------------------------------------------------------------------------ */
+int an_bn_finalize(const float* stats_part, int rows, int C, double count, const float* gamma,
+                   const float* beta, float* running_mean, float* running_var, float momentum,
+                   float eps, float* mean, float* rstd, float* scale, float* shift, void* stream);
+int an_bn_bwd_finalize(const float* stats_part, int rows, int C, double count, const float* gamma,
+                       const float* mean, const float* rstd, float* dgamma, float* dbeta, float* ca,
+                       float* cb, float* cc, void* stream);
+int an_affine_act(const void* x1, long long ld1, const void* x2, long long ld2, const float* a1,
+                  const float* a2, const float* a3, int act, void* out, long long ldo, long long M,
+                  int C, void* stream);
+int an_col_reduce_rows(long long M, int C);
+int an_col_reduce(const void* g, long long ldg, const void* x, long long ldx, const float* mean,
+                  const float* rstd, long long M, int C, float* stats_part, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Network ends: stem conv 3x3/s2 on the fp32 NCHW input (models/mobilenet_supernet.py:126-132),
+ * head BN+act fused into the global average pool (+ dropout) (:154-161), label-smoothed cross
+ * entropy (utils/optim.py:199-207; loss per sample, dlogits scaled by grad_scale).
+ * ------------------------------------------------------------------------------------------ */
+int an_stem_fwd(const float* x, const float* w, void* y, long long ldy, float* stats_part, int B,
+                int H, int W, int C, void* stream);
+int an_stem_fwd_stats_rows(int B, int Ho, int Wo);
+int an_stem_wgrad(const float* x, const void* g, long long ldg, const void* sraw, long long lds,
+                  const float* ca, const float* cb, const float* cc, float* partials, float* dw,
+                  int B, int H, int W, int C, void* stream);
+int an_stem_wgrad_rows(int B, int Ho, int Wo);
+int an_pool_fwd(const void* h, long long ldh, const float* scale, const float* shift, int act,
+                void* pooled, long long ldp, int B, int HW, int C, float drop_p,
+                unsigned long long seed, void* stream);
+int an_pool_bwd(const void* dpooled, long long ldd, const void* h, long long ldh, const float* scale,
+                const float* shift, const float* mean, const float* rstd, int act, void* gh,
+                long long ldg, float* stats_part, int B, int HW, int C, float drop_p,
+                unsigned long long seed, void* stream);
+int an_pool_bwd_stats_rows(int B);
+int an_ce_loss(const float* logits, long long ldl, const long long* labels, int B, int NC,
+               float label_smoothing, float grad_scale, float* loss, void* dlogits, long long ldd,
+               int nd_pad, void* stream);
+int an_f32_to_bf16(const float* src, long long lds, void* dst, long long ldd, long long rows,
+                   int cols, int cols_pad, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused optimizer over flat arenas (every tensor starts at a multiple of 256 elements; wd_flag /
+ * l1_pen hold one value per 256-element chunk):
+ *   g' = g*grad_scale + weight_decay*wd_flag*p + rho*l1_pen*sign(p)
+ *   RMSprop (utils/rmsprop.py:100-130), then ema = d*ema + (1-d)*p (utils/optim.py:64-65).
+ * an_refresh_weights re-materialises the kernel-layout weight copies (bf16 [N,K], bf16 [K,N]
+ * transposes for dgrad, fp32 tap-major depthwise) from the fp32 master arena via a table of
+ * 8 x int64 entries {src_off, dst_off, rows, cols, dst_ld, transpose, dst_f32, first_tile}.
+ * an_gather_rows is the bit-exact `rhs[mask]` of models/compress_utils.py:31-37.
+ * ------------------------------------------------------------------------------------------ */
+int an_rmsprop_ema_step(float* p, const float* g, float* sq, float* buf, float* ema,
+                        const float* wd_flag, const float* l1_pen, long long n, float lr,
+                        float alpha, float momentum, float eps, int eps_inside_sqrt,
+                        float grad_scale, float weight_decay, float rho, float ema_decay,
+                        void* stream);
+int an_ema_update(float* ema, const float* x, long long n, float decay, void* stream);
+int an_reg_losses(const float* p, const float* wd_flag, const float* l1_pen, long long n,
+                  float* part, void* stream);
+int an_refresh_weights(const void* table, int n_entries, long long total_tiles, const float* src,
+                       void* dst_bf16, float* dst_f32, void* stream);
+int an_gather_rows(const float* src, const long long* idx, long long n_out, long long inner,
+                   float* dst, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
