@@ -67,7 +67,12 @@ SIGNATURES = {
     "an_pw_gemm_stats_rows": (c_int, [c_int, c_int]),
     "an_pw_wgrad_splits": (c_int, [c_int, c_int, c_int]),
     "an_pw_wgrad": (c_int, [ctypes.POINTER(PwWgradArgs), c_vp]),
-    "an_wgrad_reduce": (c_int, [c_fp, c_int, c_int, c_int, c_fp, c_ll, c_ll, c_vp]),
+    "an_wgrad_reduce": (c_int, [c_fp, c_int, c_int, c_int, c_int, c_int, c_int, c_fp, c_ll, c_ll,
+                                c_vp]),
+    "an_bn_eval_coeffs": (c_int, [c_fp, c_fp, c_fp, c_fp, c_f, c_int, c_fp, c_fp, c_vp]),
+    "an_act_bwd_reduce": (c_int, [c_vp, c_ll, c_vp, c_ll, c_fp, c_fp, c_fp, c_fp, c_int, c_vp, c_ll,
+                                  c_ll, c_int, c_fp, c_vp]),
+    "an_sum_rows": (c_int, [c_fp, c_int, c_ll, c_ll, c_fp, c_vp]),
     "an_dw_fwd": (c_int, [ctypes.POINTER(DwFwdArgs), c_vp]),
     "an_dw_fwd_stats_rows": (c_int, [c_int] * 6),
     "an_dw_bwd_data": (c_int, [ctypes.POINTER(DwBwdArgs), c_vp]),

@@ -163,6 +163,87 @@ __global__ void col_reduce_kernel(const __nv_bfloat16* __restrict__ g, long long
   }
 }
 
+// eval-mode BN: scale/shift from the running statistics (F.batch_norm(training=False)).
+__global__ void bn_eval_coeffs_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      const float* __restrict__ rm, const float* __restrict__ rv,
+                                      float eps, int C, float* scale, float* shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float sc = (gamma ? gamma[c] : 1.f) * rsqrtf(rv[c] + eps);
+  scale[c] = sc;
+  shift[c] = (beta ? beta[c] : 0.f) - rm[c] * sc;
+}
+
+// g = dy * act'(scale*x + shift) (rounded to bf16, written to gout) and the partials of
+// sum(g), sum(g*xhat): activation backward + BN-backward reductions for a layer whose consumer
+// delivered a plain gradient (stem).
+__global__ void act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, long long ldy,
+                                      const __nv_bfloat16* __restrict__ x, long long ldx,
+                                      const float* __restrict__ scale, const float* __restrict__ shift,
+                                      const float* __restrict__ mean, const float* __restrict__ rstd,
+                                      int act, __nv_bfloat16* gout, long long ldg, long long M, int C,
+                                      int rows_per_cta, float* part) {
+  __shared__ float red[kRedThreads * 16];
+  const int ncg = C / 8;
+  const int cgb = min(ncg, 32);
+  const int lanes = kRedThreads / cgb;
+  const int lcg = threadIdx.x % cgb, rl = threadIdx.x / cgb;
+  const int cg = blockIdx.y * cgb + lcg;
+  const int ch = cg * 8;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) { s1[c] = 0.f; s2[c] = 0.f; }
+  if (cg < ncg && rl < lanes) {
+    float sc[8], sh[8], mu[8], rs[8];
+    load_coef8(scale, ch, C, sc, 1.f);
+    load_coef8(shift, ch, C, sh, 0.f);
+    load_coef8(mean, ch, C, mu, 0.f);
+    load_coef8(rstd, ch, C, rs, 1.f);
+    const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
+    const long long r1 = min(M, r0 + rows_per_cta);
+    for (long long r = r0 + rl; r < r1; r += lanes) {
+      const uint4 dv = ldg_nc_v4(dy + r * ldy + ch);
+      const uint4 xv = ldg_nc_v4(x + r * ldx + ch);
+      const uint32_t di[4] = {dv.x, dv.y, dv.z, dv.w}, xi[4] = {xv.x, xv.y, xv.z, xv.w};
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float d = (e & 1) ? bf16_hi(di[e >> 1]) : bf16_lo(di[e >> 1]);
+        const float xx = (e & 1) ? bf16_hi(xi[e >> 1]) : bf16_lo(xi[e >> 1]);
+        const float gq = round_bf16(d * act_bwd(fmaf(sc[e], xx, sh[e]), act));
+        o[e] = gq;
+        s1[e] += gq;
+        s2[e] = fmaf(gq, (xx - mu[e]) * rs[e], s2[e]);
+      }
+      stg_v4(gout + r * ldg + ch,
+             make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7])));
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    red[threadIdx.x * 16 + c] = s1[c];
+    red[threadIdx.x * 16 + 8 + c] = s2[c];
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < cgb * 16; o += kRedThreads) {
+    const int l = o / 16, e = o % 16;
+    float a = 0.f;
+    for (int r = 0; r < lanes; ++r) a += red[(r * cgb + l) * 16 + e];
+    const int c = (blockIdx.y * cgb + l) * 8 + (e & 7);
+    if (c < C) part[(static_cast<long long>(blockIdx.x) * 2 + (e >> 3)) * C + c] = a;
+  }
+}
+
+// dst[i] = sum_r part[r*row_stride + i]
+__global__ void sum_rows_strided_kernel(const float* __restrict__ part, int rows, long long row_stride,
+                                        long long n, float* dst) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  double a = 0.0;
+  for (int r = 0; r < rows; ++r) a += static_cast<double>(part[r * row_stride + i]);
+  dst[i] = static_cast<float>(a);
+}
+
 static int col_reduce_rows_per_cta(long long M, int C) {
   const int ncg = C / 8, cgb = ncg < 32 ? ncg : 32;
   const int ygrid = (ncg + cgb - 1) / cgb;
@@ -230,6 +311,41 @@ extern "C" int an_col_reduce(const void* g, long long ldg, const void* x, long l
   col_reduce_kernel<<<grid, kRedThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(g), ldg, reinterpret_cast<const __nv_bfloat16*>(x), ldx, mean,
       rstd, M, C, rpc, stats_part);
+  AN_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int an_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean,
+                                 const float* running_var, float eps, int C, float* scale,
+                                 float* shift, void* stream) {
+  AN_REQUIRE(running_mean && running_var && scale && shift && C > 0, "an_bn_eval_coeffs: bad arguments");
+  bn_eval_coeffs_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      gamma, beta, running_mean, running_var, eps, C, scale, shift);
+  AN_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int an_act_bwd_reduce(const void* dy, long long ldy, const void* x, long long ldx,
+                                 const float* scale, const float* shift, const float* mean,
+                                 const float* rstd, int act, void* g, long long ldg, long long M, int C,
+                                 float* stats_part, void* stream) {
+  AN_REQUIRE(dy && x && g && stats_part && scale && shift && mean && rstd && M > 0 && C > 0 && C % 8 == 0 &&
+                 ldy % 8 == 0 && ldx % 8 == 0 && ldg % 8 == 0, "an_act_bwd_reduce: bad arguments");
+  const int rpc = col_reduce_rows_per_cta(M, C);
+  const int ncg = C / 8, cgb = ncg < 32 ? ncg : 32;
+  dim3 grid(static_cast<unsigned>((M + rpc - 1) / rpc), (ncg + cgb - 1) / cgb);
+  act_bwd_reduce_kernel<<<grid, kRedThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dy), ldy, reinterpret_cast<const __nv_bfloat16*>(x), ldx, scale,
+      shift, mean, rstd, act, reinterpret_cast<__nv_bfloat16*>(g), ldg, M, C, rpc, stats_part);
+  AN_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int an_sum_rows(const float* part, int rows, long long row_stride, long long n, float* dst,
+                           void* stream) {
+  AN_REQUIRE(part && dst && rows > 0 && n > 0, "an_sum_rows: bad arguments");
+  sum_rows_strided_kernel<<<static_cast<int>((n + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      part, rows, row_stride, n, dst);
   AN_CHECK_LAUNCH();
   return 0;
 }

@@ -12,8 +12,8 @@
 
 namespace an {
 
-// Arena convention: every tensor starts at a multiple of 256 elements; wd_flag / l1_pen hold one
-// value per 256-element chunk.
+// Arena convention: wd_flag / l1_pen are per-element arrays parallel to the arena (wd_flag: 1 =
+// L2-regularised, 0 = not, < 0 = frozen padding element that must never move); n % 4 == 0.
 __global__ void rmsprop_ema_kernel(float* __restrict__ p, const float* __restrict__ g,
                                    float* __restrict__ sq, float* __restrict__ buf,
                                    float* __restrict__ ema, const float* __restrict__ wd_flag,
@@ -23,9 +23,9 @@ __global__ void rmsprop_ema_kernel(float* __restrict__ p, const float* __restric
                                    float ema_decay) {
   const long long i4 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 4;
   if (i4 >= n) return;
-  const long long chunk = i4 >> 8;
-  const float wd = weight_decay * wd_flag[chunk];
-  const float l1 = rho * l1_pen[chunk];
+  const float4 wf = *reinterpret_cast<const float4*>(wd_flag + i4);
+  const float4 lp = *reinterpret_cast<const float4*>(l1_pen + i4);
+  const float wfl[4] = {wf.x, wf.y, wf.z, wf.w}, lpe[4] = {lp.x, lp.y, lp.z, lp.w};
   float4 pv = *reinterpret_cast<float4*>(p + i4);
   const float4 gv = *reinterpret_cast<const float4*>(g + i4);
   float4 sv = *reinterpret_cast<float4*>(sq + i4);
@@ -35,8 +35,9 @@ __global__ void rmsprop_ema_kernel(float* __restrict__ p, const float* __restric
   float ss[4] = {sv.x, sv.y, sv.z, sv.w}, bb[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
+    if (wfl[k] < 0.f) continue;
     const float sgn = static_cast<float>(pp[k] > 0.f) - static_cast<float>(pp[k] < 0.f);
-    const float gr = gg[k] * grad_scale + wd * pp[k] + l1 * sgn;
+    const float gr = gg[k] * grad_scale + weight_decay * wfl[k] * pp[k] + rho * lpe[k] * sgn;
     ss[k] = ss[k] * alpha + (1.f - alpha) * gr * gr;
     const float avg = eps_inside_sqrt ? sqrtf(ss[k] + eps) : sqrtf(ss[k]) + eps;
     if (momentum > 0.f) {
@@ -71,8 +72,8 @@ __global__ void reg_loss_kernel(const float* __restrict__ p, const float* __rest
   double a = 0.0, b = 0.0;
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += gridDim.x * 256LL) {
     const float v = p[i];
-    a += static_cast<double>(wd_flag[i >> 8]) * v * v;
-    b += static_cast<double>(l1_pen[i >> 8]) * fabsf(v);
+    a += static_cast<double>(fmaxf(wd_flag[i], 0.f)) * v * v;
+    b += static_cast<double>(l1_pen[i]) * fabsf(v);
   }
   r0[threadIdx.x] = a;
   r1[threadIdx.x] = b;
@@ -87,8 +88,9 @@ __global__ void reg_loss_kernel(const float* __restrict__ p, const float* __rest
 // ------------------------------------------------------------------------------------------------
 // weight refresh: table-driven strided 2-D copy/cast/transposes, master fp32 -> kernel layouts
 // ------------------------------------------------------------------------------------------------
-struct RefreshEntry {     // mirrored by atomnas_b200/engine.py (8 x int64)
-  long long src_off;      // elements into the fp32 master arena; matrix is [rows, cols] row-major
+struct RefreshEntry {     // mirrored by atomnas_b200/engine.py (9 x int64)
+  long long src_ld;       // source pitch (elements)
+  long long src_off;      // elements into the fp32 source arena; matrix is [rows, cols], pitch src_ld
   long long dst_off;      // elements into the destination arena (bf16 or fp32)
   long long rows, cols;
   long long dst_ld;       // destination pitch (elements)
@@ -113,7 +115,7 @@ __global__ void refresh_kernel(const RefreshEntry* __restrict__ table, int n_ent
   const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
   for (int j = ty; j < 32; j += 8) {
     const long long r = r0 + j, c = c0 + tx;
-    tile[j][tx] = (r < e.rows && c < e.cols) ? src[e.src_off + r * e.cols + c] : 0.f;
+    tile[j][tx] = (r < e.rows && c < e.cols) ? src[e.src_off + r * e.src_ld + c] : 0.f;
   }
   __syncthreads();
   for (int j = ty; j < 32; j += 8) {
@@ -148,7 +150,7 @@ extern "C" int an_rmsprop_ema_step(float* p, const float* g, float* sq, float* b
                                    float alpha, float momentum, float eps, int eps_inside_sqrt,
                                    float grad_scale, float weight_decay, float rho, float ema_decay,
                                    void* stream) {
-  AN_REQUIRE(p && g && sq && wd_flag && l1_pen && n > 0 && n % 256 == 0, "an_rmsprop_ema_step: arena must be a multiple of 256 elements");
+  AN_REQUIRE(p && g && sq && wd_flag && l1_pen && n > 0 && n % 4 == 0, "an_rmsprop_ema_step: arena must be a multiple of 4 elements");
   AN_REQUIRE(momentum <= 0.f || buf, "an_rmsprop_ema_step: momentum needs a buffer");
   const long long threads = n / 4;
   rmsprop_ema_kernel<<<static_cast<int>((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(

@@ -518,15 +518,18 @@ pw_wgrad_kernel(const __grid_constant__ WgradDev p) {
   }
 }
 
+// dst[(cb-row0)*sb + cs*ss] = sum_s partials[s][cb][cs] for cb in [row0, row0+nrows), cs < ncols
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partials, int splits, int Cbig,
-                                    int Csmall, float* __restrict__ dst, long long sb,
-                                    long long ss) {
-  const long long n = static_cast<long long>(Cbig) * Csmall;
+                                    int Csmall, int row0, int nrows, int ncols,
+                                    float* __restrict__ dst, long long sb, long long ss) {
+  const long long full = static_cast<long long>(Cbig) * Csmall;
+  const long long n = static_cast<long long>(nrows) * ncols;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long cb = i / ncols, cs = i % ncols;
+    const long long src = (row0 + cb) * Csmall + cs;
     float acc = 0.f;
-    for (int s = 0; s < splits; ++s) acc += partials[s * n + i];
-    const long long cb = i / Csmall, cs = i % Csmall;
+    for (int s = 0; s < splits; ++s) acc += partials[s * full + src];
     dst[cb * sb + cs * ss] = acc;
   }
 }
@@ -681,13 +684,15 @@ extern "C" int an_pw_wgrad(const an_pw_wgrad_args* a, void* stream) {
   return 0;
 }
 
-extern "C" int an_wgrad_reduce(const float* partials, int splits, int Cbig, int Csmall, float* dst,
-                               long long dst_sb, long long dst_ss, void* stream) {
-  AN_REQUIRE(partials && dst && splits > 0, "an_wgrad_reduce: bad arguments");
-  const long long n = static_cast<long long>(Cbig) * Csmall;
+extern "C" int an_wgrad_reduce(const float* partials, int splits, int Cbig, int Csmall, int row0,
+                               int nrows, int ncols, float* dst, long long dst_sb, long long dst_ss,
+                               void* stream) {
+  AN_REQUIRE(partials && dst && splits > 0 && row0 >= 0 && nrows > 0 && row0 + nrows <= Cbig && ncols > 0 &&
+                 ncols <= Csmall, "an_wgrad_reduce: bad arguments");
+  const long long n = static_cast<long long>(nrows) * ncols;
   int blocks = static_cast<int>((n + 255) / 256);
   if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
-  wgrad_reduce_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(partials, splits, Cbig, Csmall, dst, dst_sb, dst_ss);
+  wgrad_reduce_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(partials, splits, Cbig, Csmall, row0, nrows, ncols, dst, dst_sb, dst_ss);
   AN_CHECK_LAUNCH();
   return 0;
 }

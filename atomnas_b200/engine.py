@@ -1,0 +1,825 @@
+"""Execution engine: runs an AtomNAS network (or a single block) on the sm_100a kernels.
+
+This is the host side of the hot path `model(input)` -> `loss.backward()` -> `optimizer.step()`
+(train.py:174-236 of the reference).  It owns
+
+  * the data layout in HBM: fp32 master parameter / gradient / optimizer-state arenas (the
+    nn.Parameters of the module tree are re-pointed to views of the arena), bf16 kernel-layout
+    weight copies, NHWC bf16 activation buffers, fp32 BatchNorm work vectors;
+  * the launch sequence of the kernels in csrc/ for forward, backward and the fused optimizer.
+
+Channel padding: every branch occupies a slot of roundup8(width) channels inside the branch-fused
+tensors, so arbitrary (pruned / searched) widths run on the same kernels; pad channels carry zero
+weights, gamma = beta = 0 and are frozen in the optimizer.
+
+PyTorch is used for device memory, streams and autograd plumbing only.  There is no CPU path.
+"""
+import math
+import weakref
+
+import torch
+from torch import nn
+
+from . import kernels as K
+from . import mobilenet_base as mb
+
+_BF16 = torch.bfloat16
+
+
+def _r8(n):
+    return (n + 7) // 8 * 8
+
+
+class _Arena(object):
+    """Offset allocator for one flat tensor."""
+
+    def __init__(self, align=8):
+        self.n, self.align = 0, align
+
+    def add(self, numel, align=None):
+        a = self.align if align is None else align
+        off = (self.n + a - 1) // a * a
+        self.n = off + numel
+        return off
+
+    def size(self, mult=8):
+        return max(mult, (self.n + mult - 1) // mult * mult)
+
+
+class BNGroup(object):
+    """One BatchNorm as the kernels see it: possibly several nn.BatchNorm2d fused along channels
+    (the three branches of a block), each in a slot of roundup8(width) channels."""
+
+    def __init__(self, members):
+        self.members = members                      # [(nn.BatchNorm2d, slot offset)]
+        last, off = members[-1]
+        self.C = off + _r8(last.num_features)
+        self.eps = members[0][0].eps
+        self.momentum = members[0][0].momentum
+        self.count = 0.0                            # elements per channel of the last forward
+
+
+class BlockPlan(object):
+    pass
+
+
+class Engine(object):
+    """Arenas + launch sequences for one root module (a network or a single block)."""
+
+    def __init__(self, root):
+        self.root_ref = weakref.ref(root)
+        self.is_net = hasattr(root, "features") and hasattr(root, "classifier")
+        p0 = next(root.parameters())
+        if not p0.is_cuda:
+            raise RuntimeError("atomnas_b200: the B200 engine needs CUDA tensors (no CPU fallback); "
+                               "call model.cuda() first")
+        self.dev = p0.device
+        self.bufs = {}
+        self.opt = None
+        self._build(root)
+
+    # ------------------------------------------------------------------------------------------
+    # construction: arenas, plans, refresh table
+    # ------------------------------------------------------------------------------------------
+    def _build(self, root):
+        self.pa, self.sa, self.wa16, self.wa32, self.va = _Arena(), _Arena(), _Arena(), _Arena(), _Arena()
+        self.param_slots = []       # (nn.Parameter, offset, numel, wd flag, l1 penalty)
+        self.buf_slots = []         # (module, attr, offset, numel)
+        self.bn_groups = []
+        self.refresh = []           # [src_ld, src_off, dst_off, rows, cols, dst_ld, transpose, dst_f32]
+        self.modules = set()
+        if self.is_net:
+            feats = list(root.features.children())
+            self.stem = self._plan_stem(feats[0])
+            self.blocks = [self._plan_block(b, "features.%d" % (i + 1)) for i, b in enumerate(feats[1:-2])]
+            self.head = self._plan_head(feats[-2], root.classifier)
+            self.pool_size = feats[-1].kernel_size if isinstance(feats[-1].kernel_size, int) else feats[-1].kernel_size[0]
+            self.drop_p = float(root.classifier[0].p)
+            self.drop_mod = root.classifier[0]
+        else:
+            self.stem, self.head = None, None
+            self.blocks = [self._plan_block(root, "block")]
+        for m in root.modules():
+            self.modules.add(id(m))
+        self._allocate()
+
+    def _slot(self, param, wd, l1=0.0, align=8):
+        off = self.pa.add(param.numel(), align)
+        self.param_slots.append((param, off, param.numel(), wd, l1))
+        return off
+
+    def _bn_group(self, bns):
+        """bns: list of nn.BatchNorm2d (branches).  Reserves fused gamma/beta/running-stat vectors."""
+        members, off = [], 0
+        for bn in bns:
+            members.append((bn, off))
+            off += _r8(bn.num_features)
+        g = BNGroup(members)
+        g.g_off = self.pa.add(g.C)
+        g.b_off = self.pa.add(g.C)
+        g.rm_off = self.sa.add(g.C)
+        g.rv_off = self.sa.add(g.C)
+        for bn, o in members:
+            h = bn.num_features
+            self.param_slots.append((bn.weight, g.g_off + o, h, 0.0, 0.0))
+            self.param_slots.append((bn.bias, g.b_off + o, h, 0.0, 0.0))
+            self.buf_slots.append((bn, "running_mean", g.rm_off + o, h))
+            self.buf_slots.append((bn, "running_var", g.rv_off + o, h))
+        g.v_off = self.va.add(7 * g.C)            # mean rstd scale shift ca cb cc
+        self.bn_groups.append(g)
+        return g
+
+    def _gemm_weight(self, rows, cols):
+        """Reserve bf16 [rows, cols] and its transpose [cols, rows] (rows/cols already padded)."""
+        return self.wa16.add(rows * cols), self.wa16.add(rows * cols)
+
+    def _plan_stem(self, m):
+        conv, bn = m[0], m[1]
+        s = BlockPlan()
+        s.mod, s.conv, s.C = m, conv, conv.out_channels
+        if s.C % 8 or s.C > 32:
+            raise NotImplementedError("stem width %d: sm_100a stem kernel needs a multiple of 8 <= 32" % s.C)
+        s.act = _act_of(m[2])
+        s.w_off = self._slot(conv.weight, 1.0)
+        s.bn = self._bn_group([bn])
+        return s
+
+    def _plan_block(self, b, name):
+        if type(b).__name__ == "InvertedResidualChannelsFused" or not isinstance(b, mb.InvertedResidualChannels):
+            raise NotImplementedError("block type %s has no sm_100a path yet" % type(b).__name__)
+        p = BlockPlan()
+        p.mod, p.name = b, name
+        p.inp, p.oup, p.stride, p.expand = b.input_dim, b.output_dim, b.stride, b.expand
+        if p.inp % 8 or p.oup % 8:
+            raise NotImplementedError("block in/out widths must be multiples of 8 (round_nearest=8)")
+        p.res = b.use_res_connect
+        p.act = mb.active_fn_id(b.active_fn)
+        p.channels = list(b.channels)
+        p.branches = []
+        off = 0
+        d = 1 if b.expand else 0
+        for op, h, k in zip(b.ops, b.channels, b.kernel_sizes):
+            br = BlockPlan()
+            br.h, br.hp, br.off, br.k = h, _r8(h), off, k
+            br.dw_conv, br.dw_bn, br.proj = op[d][0], op[d][1], op[d + 1]
+            if b.expand:
+                br.ex_conv, br.ex_bn = op[0][0], op[0][1]
+            off += br.hp
+            p.branches.append(br)
+        p.Kh = off
+        if not p.branches:
+            return p
+        if b.expand:
+            for br in p.branches:
+                br.we_off = self._slot(br.ex_conv.weight, 1.0)
+            p.bn_e = self._bn_group([br.ex_bn for br in p.branches])
+            p.we16, p.weT16 = self._gemm_weight(p.Kh, p.inp)
+            for br in p.branches:
+                self.refresh.append([p.inp, br.we_off, p.we16 + br.off * p.inp, br.h, p.inp, p.inp, 0, 0])
+                self.refresh.append([p.inp, br.we_off, p.weT16 + br.off, br.h, p.inp, p.Kh, 1, 0])
+        else:
+            if p.Kh != p.inp:
+                raise NotImplementedError("non-expanding block with padded width")
+        for br in p.branches:
+            br.wd_off = self._slot(br.dw_conv.weight, 1.0)
+            br.wd32 = self.wa32.add(br.k * br.k * br.hp)
+            self.refresh.append([br.k * br.k, br.wd_off, br.wd32, br.h, br.k * br.k, br.hp, 1, 1])
+        p.bn_d = self._bn_group([br.dw_bn for br in p.branches])
+        for br in p.branches:
+            br.wp_off = self._slot(br.proj.weight, 1.0)
+        p.wp16, p.wpT16 = self._gemm_weight(p.oup, p.Kh)
+        for br in p.branches:
+            self.refresh.append([br.h, br.wp_off, p.wp16 + br.off, p.oup, br.h, p.Kh, 0, 0])
+            self.refresh.append([br.h, br.wp_off, p.wpT16 + br.off * p.oup, p.oup, br.h, p.oup, 1, 0])
+        p.bn_p = self._bn_group([b.pw_bn])
+        return p
+
+    def _plan_head(self, m, classifier):
+        conv, bn, fc = m[0], m[1], classifier[1]
+        h = BlockPlan()
+        h.mod, h.cin, h.C = m, conv.in_channels, conv.out_channels
+        if h.C % 8 or h.cin % 8:
+            raise NotImplementedError("head widths must be multiples of 8")
+        h.act = _act_of(m[2])
+        h.w_off = self._slot(conv.weight, 1.0)
+        h.bn = self._bn_group([bn])
+        h.w16, h.wT16 = self._gemm_weight(h.C, h.cin)
+        self.refresh.append([h.cin, h.w_off, h.w16, h.C, h.cin, h.cin, 0, 0])
+        self.refresh.append([h.cin, h.w_off, h.wT16, h.C, h.cin, h.C, 1, 0])
+        h.fc, h.NC, h.NCp = fc, fc.out_features, _r8(fc.out_features)
+        h.fw_off = self._slot(fc.weight, 1.0)
+        h.fb_off = self.pa.add(h.NCp)
+        self.param_slots.append((fc.bias, h.fb_off, h.NC, 1.0, 0.0))
+        h.fw16, h.fwT16 = self._gemm_weight(h.NCp, h.C)
+        self.refresh.append([h.C, h.fw_off, h.fw16, h.NC, h.C, h.C, 0, 0])
+        self.refresh.append([h.C, h.fw_off, h.fwT16, h.NC, h.C, h.NCp, 1, 0])
+        return h
+
+    def _allocate(self):
+        dev = self.dev
+        n = self.pa.size()
+        self.n_params = n
+        self.P = torch.zeros(n, device=dev)
+        self.G = torch.zeros(n, device=dev)
+        self.S = torch.zeros(self.sa.size(), device=dev)
+        self.W16 = torch.zeros(self.wa16.size(), device=dev, dtype=_BF16)
+        self.W32 = torch.zeros(self.wa32.size(), device=dev)
+        self.V = torch.zeros(self.va.size(), device=dev)
+        self.wd_flag = torch.full((n,), -1.0, device=dev)        # everything not claimed = frozen pad
+        self.l1_pen = torch.zeros(n, device=dev)
+        with torch.no_grad():
+            for g in self.bn_groups:                              # pads: running_var = 1
+                self.S[g.rv_off:g.rv_off + g.C] = 1.0
+            for prm, off, numel, wd, l1 in self.param_slots:
+                view = self.P[off:off + numel].view(prm.shape)
+                view.copy_(prm.data)
+                prm.data = view
+                self.wd_flag[off:off + numel] = wd
+                self.l1_pen[off:off + numel] = l1
+            for mod, attr, off, numel in self.buf_slots:
+                t = getattr(mod, attr)
+                view = self.S[off:off + numel]
+                view.copy_(t)
+                t.data = view
+            bns = [m for g in self.bn_groups for m, _ in g.members]
+            self.NBT = torch.zeros(max(1, len(bns)), dtype=torch.int64, device=dev)
+            for i, m in enumerate(bns):
+                if m.num_batches_tracked is not None:
+                    self.NBT[i] = m.num_batches_tracked
+                    m.num_batches_tracked.data = self.NBT[i]
+        tiles, table = 0, []
+        for e in self.refresh:
+            table.append(e + [tiles])
+            tiles += ((e[3] + 31) // 32) * ((e[4] + 31) // 32)
+        self.refresh_tiles = tiles
+        self.refresh_table = (torch.tensor(table, dtype=torch.int64, device=dev)
+                              if table else None)
+        self.weights_version = -1
+        self.grad_views = None
+
+    # ---- small accessors ----------------------------------------------------------------------
+    def _bnv(self, g, i):
+        return self.V[g.v_off + i * g.C: g.v_off + (i + 1) * g.C]
+
+    def bn_vec(self, g, name):
+        return self._bnv(g, ("mean", "rstd", "scale", "shift", "ca", "cb", "cc").index(name))
+
+    def gamma(self, g): return self.P[g.g_off:g.g_off + g.C]
+    def beta(self, g): return self.P[g.b_off:g.b_off + g.C]
+    def dgamma(self, g): return self.G[g.g_off:g.g_off + g.C]
+    def dbeta(self, g): return self.G[g.b_off:g.b_off + g.C]
+    def rmean(self, g): return self.S[g.rm_off:g.rm_off + g.C]
+    def rvar(self, g): return self.S[g.rv_off:g.rv_off + g.C]
+
+    def params(self):
+        """Parameters in arena order (the order autograd gradients are returned in)."""
+        return [s[0] for s in self.param_slots]
+
+    def param_grad_views(self):
+        if self.grad_views is None:
+            self.grad_views = [self.G[off:off + n].view(p.shape) for p, off, n, _, _ in self.param_slots]
+        return self.grad_views
+
+    def set_l1_penalties(self, named_penalties, named_params):
+        """Mark prunable gammas: l1_pen[elements of param `name`] = penalty (utils/prune.py:112-123)."""
+        by_id = {id(p): (off, n) for p, off, n, _, _ in self.param_slots}
+        self.l1_pen.zero_()
+        for name, pen in named_penalties:
+            off, n = by_id[id(named_params[name])]
+            self.l1_pen[off:off + n] = float(pen)
+
+    def refresh_weights(self, force=False):
+        """Re-materialise bf16 / transposed / tap-major weight copies from the fp32 masters."""
+        ver = sum(p._version for p, _, _, _, _ in self.param_slots if p.dim() > 1)
+        if not force and ver == self.weights_version:
+            return
+        if self.refresh_table is not None:
+            K.refresh_weights(self.refresh_table, len(self.refresh), self.refresh_tiles, self.P, self.W16, self.W32)
+        self.weights_version = ver
+
+    # ------------------------------------------------------------------------------------------
+    # per-shape buffers
+    # ------------------------------------------------------------------------------------------
+    def _buffers(self, B, H, W, need_grad):
+        key = (B, H, W, need_grad)
+        if key in self.bufs:
+            return self.bufs[key]
+        dev = self.dev
+        bf = _Buf()
+        bf.B = B
+        part_max, wpart_max = 8, 8
+        big_e, big_d, big_y = 8, 8, 8
+
+        def bf16(*shape):
+            return torch.empty(shape, device=dev, dtype=_BF16)
+
+        h, w = H, W
+        if self.is_net:
+            s = self.stem
+            h, w = (H + 1) // 2, (W + 1) // 2
+            bf.s_hw = (h, w)
+            bf.s_raw = bf16(B * h * w, s.C)
+            bf.y0 = bf16(B * h * w, s.C)
+            part_max = max(part_max, K.stem_fwd_stats_rows(B, h, w) * 2 * s.C,
+                           K.col_reduce_rows(B * h * w, s.C) * 2 * s.C)
+            wpart_max = max(wpart_max, K.stem_wgrad_rows(B, h, w) * s.C * 27)
+            big_y = max(big_y, B * h * w * s.C)
+        bf.blk = []
+        for p in self.blocks:
+            bb = _Buf()
+            bb.hin, bb.win = h, w
+            ho, wo = ((h + 1) // 2, (w + 1) // 2) if p.stride == 2 else (h, w)
+            bb.ho, bb.wo = ho, wo
+            M, Mo = B * h * w, B * ho * wo
+            bb.M, bb.Mo = M, Mo
+            if p.branches:
+                if p.expand:
+                    bb.e_raw = bf16(M, p.Kh)
+                    part_max = max(part_max, K.pw_gemm_stats_rows(M, p.Kh) * 2 * p.Kh)
+                    wpart_max = max(wpart_max, K.pw_wgrad_splits(M, p.Kh, p.inp) * p.Kh * p.inp)
+                    big_e = max(big_e, M * p.Kh)
+                bb.d_raw = bf16(Mo, p.Kh)
+                if any(br.hp != br.h for br in p.branches):
+                    bb.d_raw.zero_()
+                    if p.expand:
+                        bb.e_raw.zero_()
+                bb.p_raw = bf16(Mo, p.oup)
+                big_d = max(big_d, Mo * p.Kh)
+                for br in p.branches:
+                    part_max = max(part_max, K.dw_fwd_stats_rows(B, br.hp, ho, wo, br.k, p.stride) * 2 * br.hp,
+                                   K.dw_bwd_data_stats_rows(B, br.hp, h, w, br.k, p.stride) * 2 * br.hp)
+                    wpart_max = max(wpart_max, K.dw_bwd_weight_rows(B, br.hp, h, w, br.k, p.stride) * br.k * br.k * br.hp)
+                part_max = max(part_max, K.pw_gemm_stats_rows(Mo, p.oup) * 2 * p.oup,
+                               K.pw_gemm_stats_rows(Mo, p.Kh) * 2 * p.Kh,
+                               K.col_reduce_rows(Mo, p.oup) * 2 * p.oup)
+                wpart_max = max(wpart_max, K.pw_wgrad_splits(Mo, p.Kh, p.oup) * p.Kh * p.oup)
+            bb.y = bf16(Mo, p.oup)
+            big_y = max(big_y, Mo * p.oup, M * p.inp)
+            bf.blk.append(bb)
+            h, w = ho, wo
+        if self.is_net:
+            hd = self.head
+            Mh = B * h * w
+            bf.h_hw, bf.Mh = (h, w), Mh
+            if h != self.pool_size or w != self.pool_size:
+                raise NotImplementedError("global pooling only (AvgPool2d(input_size // 32))")
+            bf.h_raw = bf16(Mh, hd.C)
+            bf.pooled = bf16(B, hd.C)
+            bf.logits = torch.zeros(B, hd.NCp, device=dev)
+            part_max = max(part_max, K.pw_gemm_stats_rows(Mh, hd.C) * 2 * hd.C,
+                           K.pool_bwd_stats_rows(B) * 2 * hd.C, K.col_reduce_rows(B, hd.NCp) * 2 * hd.NCp)
+            wpart_max = max(wpart_max, K.pw_wgrad_splits(Mh, hd.C, hd.cin) * hd.C * hd.cin,
+                            K.pw_wgrad_splits(B, hd.C, hd.NCp) * hd.C * hd.NCp)
+            if need_grad:
+                bf.gh = bf16(Mh, hd.C)
+                bf.dpool = bf16(B, hd.C)
+                bf.dlogits = torch.zeros(B, hd.NCp, device=dev, dtype=_BF16)
+        bf.part = torch.empty(part_max, device=dev)
+        if need_grad:
+            bf.wpart = torch.empty(wpart_max, device=dev)
+            bf.g_d = bf16(big_d)
+            bf.g_e = bf16(big_e)
+            bf.dp = bf16(big_y)
+            bf.dy = [bf16(big_y), bf16(big_y)]
+        self.bufs = {key: bf}          # keep one shape resident (train and calibration alternate rarely)
+        return bf
+
+    # ------------------------------------------------------------------------------------------
+    # BN helpers
+    # ------------------------------------------------------------------------------------------
+    def _bn_fwd(self, g, part, rows, count, training, C=None, off=0):
+        """Finalize (training) or derive eval coefficients for channels [off, off+C) of group g."""
+        C = g.C if C is None else C
+        sl = slice(off, off + C)
+        mean, rstd = self.bn_vec(g, "mean")[sl], self.bn_vec(g, "rstd")[sl]
+        scale, shift = self.bn_vec(g, "scale")[sl], self.bn_vec(g, "shift")[sl]
+        if training:
+            mom = g.mom_now
+            K.bn_finalize(part, rows, C, count, self.gamma(g)[sl], self.beta(g)[sl], self.rmean(g)[sl],
+                          self.rvar(g)[sl], mom, g.eps, mean, rstd, scale, shift)
+            g.count = count
+        else:
+            K.bn_eval_coeffs(self.gamma(g)[sl], self.beta(g)[sl], self.rmean(g)[sl], self.rvar(g)[sl],
+                             g.eps, C, scale, shift)
+
+    def _bn_bwd(self, g, part, rows, C=None, off=0):
+        C = g.C if C is None else C
+        sl = slice(off, off + C)
+        K.bn_bwd_finalize(part, rows, C, g.count, self.gamma(g)[sl], self.bn_vec(g, "mean")[sl],
+                          self.bn_vec(g, "rstd")[sl], self.dgamma(g)[sl], self.dbeta(g)[sl],
+                          self.bn_vec(g, "ca")[sl], self.bn_vec(g, "cb")[sl], self.bn_vec(g, "cc")[sl])
+
+    def _begin_bn_step(self, training):
+        """Per-forward BN bookkeeping: num_batches_tracked and the momentum to use
+        (momentum=None => cumulative average, utils/common.py:214-226)."""
+        if training:
+            self.NBT.add_(1)              # every num_batches_tracked buffer is a view of this arena
+        for g in self.bn_groups:
+            bn = g.members[0][0]
+            if training and bn.track_running_stats:
+                g.mom_now = (1.0 / float(bn.num_batches_tracked.item())) if bn.momentum is None else bn.momentum
+            else:
+                g.mom_now = 0.0
+
+    # ------------------------------------------------------------------------------------------
+    # forward
+    # ------------------------------------------------------------------------------------------
+    def forward(self, x, training, need_grad, seed=0):
+        """x: fp32 NCHW (network) or NHWC bf16 [B,H,W,C] (single block).  Returns logits fp32
+        [B, NC] for a network, NHWC bf16 for a block."""
+        self.refresh_weights()
+        if self.is_net:
+            B, _, H, W = x.shape
+        else:
+            B, H, W, _ = x.shape
+        bf = self._buffers(B, H, W, need_grad)
+        bf.training, bf.seed = training, seed
+        self._begin_bn_step(training)
+        part = bf.part
+        stats = part if training else None
+        if self.is_net:
+            s = self.stem
+            x = x.contiguous()
+            if x.dtype != torch.float32:
+                x = x.float()
+            bf.x = x
+            h, w = bf.s_hw
+            K.stem_fwd(x, self.P[s.w_off:], bf.s_raw, stats, B, H, W, s.C, ldy=s.C)
+            self._bn_fwd(s.bn, part, K.stem_fwd_stats_rows(B, h, w), B * h * w, training)
+            K.affine_act(bf.s_raw, bf.y0, B * h * w, s.C, ld1=s.C, ldo=s.C, a1=self.bn_vec(s.bn, "scale"),
+                         a3=self.bn_vec(s.bn, "shift"), act=s.act)
+            cur = bf.y0
+        else:
+            cur = x.reshape(B * H * W, -1)
+            bf.x = cur
+        for p, bb in zip(self.blocks, bf.blk):
+            cur = self._block_fwd(p, bb, cur, B, training, stats, part)
+        if not self.is_net:
+            return cur.view(B, bf.blk[-1].ho, bf.blk[-1].wo, -1)
+        hd = self.head
+        Mh = bf.Mh
+        K.pw_gemm(cur, self.W16[hd.w16:], bf.h_raw, Mh, hd.C, hd.cin, stats_part=stats)
+        self._bn_fwd(hd.bn, part, K.pw_gemm_stats_rows(Mh, hd.C), Mh, training)
+        drop = self.drop_p if (training and self.drop_mod.training) else 0.0
+        bf.drop = drop
+        K.pool_fwd(bf.h_raw, self.bn_vec(hd.bn, "scale"), self.bn_vec(hd.bn, "shift"), hd.act, bf.pooled,
+                   B, Mh // B, hd.C, ldh=hd.C, ldp=hd.C, drop_p=drop, seed=seed)
+        K.pw_gemm(bf.pooled, self.W16[hd.fw16:], bf.logits, B, hd.NCp, hd.C, bias=self.P[hd.fb_off:])
+        return bf.logits[:, :hd.NC]
+
+    def _block_fwd(self, p, bb, x, B, training, stats, part):
+        bb.x = x
+        if not p.branches:
+            bb.y = x
+            return x
+        M, Mo = bb.M, bb.Mo
+        if p.expand:
+            K.pw_gemm(x, self.W16[p.we16:], bb.e_raw, M, p.Kh, p.inp, stats_part=stats)
+            self._bn_fwd(p.bn_e, part, K.pw_gemm_stats_rows(M, p.Kh), M, training)
+            src, ld_src = bb.e_raw, p.Kh
+            e_scale, e_shift = self.bn_vec(p.bn_e, "scale"), self.bn_vec(p.bn_e, "shift")
+        else:
+            src, ld_src, e_scale, e_shift = x, p.inp, None, None
+        for br in p.branches:
+            K.dw_fwd(src[:, br.off:], bb.d_raw[:, br.off:], self.W32[br.wd32:], B, bb.hin, bb.win, br.hp,
+                     br.k, p.stride, ldx=ld_src, ldy=p.Kh,
+                     scale=None if e_scale is None else e_scale[br.off:],
+                     shift=None if e_shift is None else e_shift[br.off:], act=p.act, stats_part=stats)
+            self._bn_fwd(p.bn_d, part, K.dw_fwd_stats_rows(B, br.hp, bb.ho, bb.wo, br.k, p.stride), Mo,
+                         training, C=br.hp, off=br.off)
+        K.pw_gemm(bb.d_raw, self.W16[p.wp16:], bb.p_raw, Mo, p.oup, p.Kh, a_mode=1, a_act=p.act,
+                  a1=self.bn_vec(p.bn_d, "scale"), a3=self.bn_vec(p.bn_d, "shift"), stats_part=stats)
+        self._bn_fwd(p.bn_p, part, K.pw_gemm_stats_rows(Mo, p.oup), Mo, training)
+        K.affine_act(bb.p_raw, bb.y, Mo, p.oup, ld1=p.oup, ldo=p.oup, x2=x if p.res else None, ld2=p.inp,
+                     a1=self.bn_vec(p.bn_p, "scale"), a3=self.bn_vec(p.bn_p, "shift"))
+        return bb.y
+
+    # ------------------------------------------------------------------------------------------
+    # backward
+    # ------------------------------------------------------------------------------------------
+    def backward(self, dout, grad_ready=None):
+        """dout: bf16 dlogits [B, NCp] already in bf.dlogits (network; pass None) or NHWC bf16 grad
+        (block).  Fills the gradient arena; returns grad wrt the block input (block mode).
+        grad_ready(offset) is called as soon as every gradient at arena offsets >= offset is final
+        (bucketed all-reduce overlap)."""
+        bf = next(iter(self.bufs.values()))
+        B = bf.B
+        part, wpart = bf.part, bf.wpart
+        G, P = self.G, self.P
+        if self.is_net:
+            hd = self.head
+            Mh = bf.Mh
+            dl = bf.dlogits
+            # classifier: dW = dlogits^T pooled, db = colsum(dlogits), dpooled = dlogits W
+            sp = K.pw_wgrad(bf.pooled, dl, wpart, B, hd.C, hd.NCp)
+            K.wgrad_reduce(wpart, sp, hd.C, hd.NCp, G[hd.fw_off:], 1, hd.C, ncols=hd.NC)
+            rows = K.col_reduce_rows(B, hd.NCp)
+            K.col_reduce(dl, part, B, hd.NCp, ldg=hd.NCp)
+            K.sum_rows(part, rows, 2 * hd.NCp, hd.NC, G[hd.fb_off:])
+            K.pw_gemm(dl, self.W16[hd.fwT16:], bf.dpool, B, hd.C, hd.NCp)
+            K.pool_bwd(bf.dpool, bf.h_raw, self.bn_vec(hd.bn, "scale"), self.bn_vec(hd.bn, "shift"),
+                       self.bn_vec(hd.bn, "mean"), self.bn_vec(hd.bn, "rstd"), hd.act, bf.gh, part, B,
+                       Mh // B, hd.C, ldd=hd.C, ldh=hd.C, ldg=hd.C, drop_p=bf.drop, seed=bf.seed)
+            self._bn_bwd(hd.bn, part, K.pool_bwd_stats_rows(B))
+            ca, cb, cc = (self.bn_vec(hd.bn, n) for n in ("ca", "cb", "cc"))
+            y_last = bf.blk[-1].y if self.blocks else bf.y0
+            sp = K.pw_wgrad(bf.gh, y_last, wpart, Mh, hd.C, hd.cin, p2=bf.h_raw, p_mode=2, a1=ca, a2=cb, a3=cc)
+            K.wgrad_reduce(wpart, sp, hd.C, hd.cin, G[hd.w_off:], hd.cin, 1)
+            dy = bf.dy[0]
+            K.pw_gemm(bf.gh, self.W16[hd.wT16:], dy, Mh, hd.cin, hd.C, x2=bf.h_raw, a_mode=2, a1=ca, a2=cb, a3=cc)
+            if grad_ready is not None:
+                grad_ready(hd.w_off)
+            slot = 0                      # dy lives in bf.dy[slot]; dx goes to the other one
+        else:
+            dy = dout.reshape(bf.blk[-1].Mo, -1)
+            slot = 1
+        for p, bb in zip(reversed(self.blocks), reversed(bf.blk)):
+            if not p.branches:
+                continue
+            dx = bf.dy[1 - slot]
+            self._block_bwd(p, bb, dy, dx, B, part, wpart, bf)
+            if grad_ready is not None:
+                grad_ready(self._block_first_offset(p))
+            dy, slot = dx, 1 - slot
+        if not self.is_net:
+            b0 = bf.blk[0]
+            return dy[:b0.M * self.blocks[0].inp].view(B, b0.hin, b0.win, -1)
+        s = self.stem
+        h, w = bf.s_hw
+        M0 = B * h * w
+        gs = bf.dp
+        K.act_bwd_reduce(dy, bf.s_raw, self.bn_vec(s.bn, "scale"), self.bn_vec(s.bn, "shift"),
+                         self.bn_vec(s.bn, "mean"), self.bn_vec(s.bn, "rstd"), s.act, gs, part, M0, s.C,
+                         ldy=s.C, ldx=s.C, ldg=s.C)
+        self._bn_bwd(s.bn, part, K.col_reduce_rows(M0, s.C))
+        K.stem_wgrad(bf.x, gs, bf.s_raw, self.bn_vec(s.bn, "ca"), self.bn_vec(s.bn, "cb"), self.bn_vec(s.bn, "cc"),
+                     wpart, G[s.w_off:], B, bf.x.shape[2], bf.x.shape[3], s.C, ldg=s.C, lds=s.C)
+        if grad_ready is not None:
+            grad_ready(0)
+        return None
+
+    def _block_first_offset(self, p):
+        br = p.branches[0]
+        return br.we_off if p.expand else br.wd_off
+
+    def _block_bwd(self, p, bb, dy, dx, B, part, wpart, bf):
+        """dy: grad wrt block output [Mo, oup]; writes grad wrt block input into dx [M, inp]."""
+        G = self.G
+        M, Mo = bb.M, bb.Mo
+        act = p.act
+        # pw_bn backward: reductions over (dy, p_raw), then dp_raw = ca*dy + cb*p_raw + cc
+        K.col_reduce(dy, part, Mo, p.oup, ldg=p.oup, x=bb.p_raw, ldx=p.oup,
+                     mean=self.bn_vec(p.bn_p, "mean"), rstd=self.bn_vec(p.bn_p, "rstd"))
+        self._bn_bwd(p.bn_p, part, K.col_reduce_rows(Mo, p.oup))
+        dp = bf.dp
+        K.affine_act(dy, dp, Mo, p.oup, ld1=p.oup, ldo=p.oup, x2=bb.p_raw, ld2=p.oup,
+                     a1=self.bn_vec(p.bn_p, "ca"), a2=self.bn_vec(p.bn_p, "cb"), a3=self.bn_vec(p.bn_p, "cc"))
+        d_scale, d_shift = self.bn_vec(p.bn_d, "scale"), self.bn_vec(p.bn_d, "shift")
+        # project weight gradient: dWp[oup, h_i] = dp^T act(bn(d_raw))
+        sp = K.pw_wgrad(bb.d_raw, dp, wpart, Mo, p.Kh, p.oup, p_mode=1, p_act=act, a1=d_scale, a3=d_shift)
+        for br in p.branches:
+            K.wgrad_reduce(wpart, sp, p.Kh, p.oup, G[br.wp_off:], 1, br.h, row0=br.off, nrows=br.h)
+        # project data gradient with act/BN backward epilogue -> g_d
+        g_d = bf.g_d
+        K.pw_gemm(dp, self.W16[p.wpT16:], g_d, Mo, p.Kh, p.oup, epi_mode=1, r=bb.d_raw, ldr=p.Kh,
+                  r_scale=d_scale, r_shift=d_shift, r_mean=self.bn_vec(p.bn_d, "mean"),
+                  r_rstd=self.bn_vec(p.bn_d, "rstd"), r_act=act, stats_part=part)
+        self._bn_bwd(p.bn_d, part, K.pw_gemm_stats_rows(Mo, p.Kh))
+        dca, dcb, dcc = (self.bn_vec(p.bn_d, n) for n in ("ca", "cb", "cc"))
+        if p.expand:
+            src, ld_src = bb.e_raw, p.Kh
+            e_scale, e_shift = self.bn_vec(p.bn_e, "scale"), self.bn_vec(p.bn_e, "shift")
+            e_mean, e_rstd = self.bn_vec(p.bn_e, "mean"), self.bn_vec(p.bn_e, "rstd")
+            ge, ld_ge = bf.g_e, p.Kh
+        else:
+            src, ld_src, e_scale, e_shift, e_mean, e_rstd = bb.x, p.inp, None, None, None, None
+            ge, ld_ge = (dx if not p.res else bf.g_e), p.inp
+
+        def sl(v, br):
+            return None if v is None else v[br.off:]
+
+        for br in p.branches:
+            o = br.off
+            if br.hp == br.h:
+                K.dw_bwd_weight(g_d[o:], bb.d_raw[:, o:], src[:, o:], dca[o:], dcb[o:], dcc[o:],
+                                sl(e_scale, br), sl(e_shift, br), act if p.expand else 0, wpart,
+                                G[br.wd_off:], B, bb.hin, bb.win, br.hp, br.k, p.stride, ldg=p.Kh, ldd=p.Kh,
+                                lde=ld_src)
+            else:
+                self._dw_wgrad_padded(p, bb, br, g_d, src, ld_src, dca, dcb, dcc, e_scale, e_shift, B, wpart)
+            K.dw_bwd_data(g_d[o:], bb.d_raw[:, o:], src[:, o:], ge[o:], self.W32[br.wd32:], dca[o:], dcb[o:],
+                          dcc[o:], sl(e_scale, br), sl(e_shift, br), sl(e_mean, br), sl(e_rstd, br),
+                          part if p.expand else None, act if p.expand else 0, B, bb.hin, bb.win, br.hp, br.k,
+                          p.stride, ldg=p.Kh, ldd=p.Kh, lde=ld_src, ldge=ld_ge)
+            if p.expand:
+                self._bn_bwd(p.bn_e, part, K.dw_bwd_data_stats_rows(B, br.hp, bb.hin, bb.win, br.k, p.stride),
+                             C=br.hp, off=o)
+        if not p.expand:
+            if p.res:
+                K.affine_act(ge, dx, M, p.inp, ld1=p.inp, ldo=p.inp, x2=dy, ld2=p.oup)
+            return
+        eca, ecb, ecc = (self.bn_vec(p.bn_e, n) for n in ("ca", "cb", "cc"))
+        sp = K.pw_wgrad(ge, bb.x, wpart, M, p.Kh, p.inp, p2=bb.e_raw, p_mode=2, a1=eca, a2=ecb, a3=ecc)
+        for br in p.branches:
+            K.wgrad_reduce(wpart, sp, p.Kh, p.inp, G[br.we_off:], p.inp, 1, row0=br.off, nrows=br.h)
+        K.pw_gemm(ge, self.W16[p.weT16:], dx, M, p.inp, p.Kh, x2=bb.e_raw, a_mode=2, a1=eca, a2=ecb, a3=ecc,
+                  epi_mode=2, r=dy if p.res else None, ldr=p.oup)
+
+    def _dw_wgrad_padded(self, p, bb, br, g_d, src, ld_src, dca, dcb, dcc, e_scale, e_shift, B, wpart):
+        """Depthwise weight gradient of a branch whose width is not a multiple of 8: run on the
+        padded slot into scratch, then keep the first h rows (pad rows are exactly zero)."""
+        o = br.off
+        tmp = torch.empty(br.hp * br.k * br.k, device=self.dev)
+        K.dw_bwd_weight(g_d[o:], bb.d_raw[:, o:], src[:, o:], dca[o:], dcb[o:], dcc[o:],
+                        None if e_scale is None else e_scale[o:], None if e_shift is None else e_shift[o:],
+                        p.act if p.expand else 0, wpart, tmp, B, bb.hin, bb.win, br.hp, br.k, p.stride,
+                        ldg=p.Kh, ldd=p.Kh, lde=ld_src)
+        n = br.h * br.k * br.k
+        self.G[br.wd_off:br.wd_off + n].copy_(tmp[:n])
+
+    # ------------------------------------------------------------------------------------------
+    # loss (network mode)
+    # ------------------------------------------------------------------------------------------
+    def loss_and_dlogits(self, target, label_smoothing, grad_scale):
+        """Label-smoothed CE per sample (utils/optim.py:199-207) and dlogits = dL/dlogits * grad_scale
+        for L = mean(loss)."""
+        bf = next(iter(self.bufs.values()))
+        hd = self.head
+        B = bf.B
+        if not hasattr(bf, "loss") or bf.loss.shape[0] != B:
+            bf.loss = torch.empty(B, device=self.dev)
+        K.ce_loss(bf.logits, target, B, hd.NC, label_smoothing, grad_scale / B, bf.loss, bf.dlogits,
+                  ldl=hd.NCp, ldd=hd.NCp, nd_pad=hd.NCp)
+        return bf.loss
+
+    def set_dlogits(self, dlogits_f32):
+        """Autograd path: take dL/dlogits [B, NC] fp32 from PyTorch and stage it as bf16 [B, NCp]."""
+        bf = next(iter(self.bufs.values()))
+        hd = self.head
+        d = dlogits_f32.contiguous()
+        K.f32_to_bf16(d, bf.dlogits, bf.B, hd.NC, hd.NCp, lds=d.shape[1], ldd=hd.NCp)
+
+
+class _Buf(object):
+    pass
+
+
+def _act_of(module):
+    if isinstance(module, nn.ReLU6):
+        return 2
+    if isinstance(module, nn.ReLU):
+        return 1
+    if isinstance(module, mb.Swish):
+        return 3
+    if isinstance(module, mb.Identity):
+        return 0
+    raise NotImplementedError("activation %r has no sm_100a kernel path" % (module,))
+
+
+# ------------------------------------------------------------------------------------------------
+# module -> engine registry, autograd glue
+# ------------------------------------------------------------------------------------------------
+_ENGINES = weakref.WeakKeyDictionary()
+
+
+def get_engine(root):
+    eng = _ENGINES.get(root)
+    if eng is not None and not _still_valid(eng, root):
+        eng = None
+    if eng is None:
+        eng = Engine(root)
+        _ENGINES[root] = eng
+    return eng
+
+
+def _still_valid(eng, root):
+    for p in eng.blocks:
+        if list(p.mod.channels) != p.channels or (p.branches and p.branches[0].proj is not p.mod.ops[0][-1]):
+            return False
+    return next(root.parameters()).device == eng.dev
+
+
+def invalidate(module):
+    """Drop every engine that contains `module` (called after a shrink rebuilt its children)."""
+    for root in list(_ENGINES.keys()):
+        if id(module) in _ENGINES[root].modules:
+            del _ENGINES[root]
+
+
+class _NetFunction(torch.autograd.Function):
+    """The whole network as ONE autograd node: forward runs the kernel sequence, backward fills
+    the gradient arena and hands PyTorch views of it."""
+
+    @staticmethod
+    def forward(ctx, eng, x, seed, *params):
+        ctx.eng = eng
+        out = eng.forward(x, True, True, seed)
+        return out.clone()
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        eng = ctx.eng
+        eng.set_dlogits(dlogits)
+        eng.backward(None)
+        return (None, None, None) + tuple(eng.param_grad_views())
+
+
+class _BlockFunction(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, eng, x_nhwc, *params):
+        ctx.eng = eng
+        return eng.forward(x_nhwc, True, True).clone()
+
+    @staticmethod
+    def backward(ctx, dy):
+        eng = ctx.eng
+        dx = eng.backward(dy.contiguous())
+        return (None, dx.clone()) + tuple(eng.param_grad_views())
+
+
+_SEED = [0x5EED]
+
+
+def run_module(module, x):
+    """forward() of the mirrored nn.Modules lands here."""
+    if not x.is_cuda:
+        raise RuntimeError("atomnas_b200: CPU tensor passed to the B200 hot path (no CPU fallback)")
+    is_net = hasattr(module, "features") and hasattr(module, "classifier")
+    if not is_net and not isinstance(module, mb.InvertedResidualChannels):
+        raise NotImplementedError("standalone %s forward is not part of the B200 hot path" % type(module).__name__)
+    eng = get_engine(module)
+    need_grad = torch.is_grad_enabled() and module.training and any(p.requires_grad for p in eng.params())
+    if is_net:
+        if need_grad:
+            _SEED[0] += 1
+            out = _NetFunction.apply(eng, x, _SEED[0], *eng.params())
+        else:
+            out = eng.forward(x, _bn_training(module), False).clone()
+        _fire_profiling_hooks(module, eng, x)
+        return out
+    # single block: NCHW fp32 API of the reference around the NHWC bf16 kernels
+    xn = x.permute(0, 2, 3, 1).contiguous().to(_BF16)
+    if need_grad or (torch.is_grad_enabled() and x.requires_grad):
+        y = _BlockFunction.apply(eng, xn, *eng.params())
+    else:
+        y = eng.forward(xn, _bn_training(module), False).clone()
+    return y.permute(0, 3, 1, 2).to(x.dtype)
+
+
+def _bn_training(module):
+    """BN uses batch statistics iff its modules are in training mode (bn_calibration flips only
+    the BatchNorm2d children to train(), utils/common.py:214-226)."""
+    for m in module.modules():
+        if isinstance(m, nn.BatchNorm2d):
+            return m.training
+    return module.training
+
+
+def _fire_profiling_hooks(model, eng, x):
+    """utils/model_profiling.py registers forward hooks on EVERY submodule and derives n_macs from
+    the hook's input/output shapes.  The engine never calls the parameter-holder children, so
+    when (and only when) hooks are present it invokes them with shape-carrying dummy tensors, in
+    depth-first order, exactly as a module-by-module forward would."""
+    feats = list(model.features.children())
+    if not any(len(m._forward_hooks) for m in model.modules()):
+        return
+
+    def fire(m, shape_in, shape_out):
+        if not m._forward_hooks:
+            return
+        i = torch.empty(shape_in, device=x.device)
+        o = torch.empty(shape_out, device=x.device)
+        for hook in list(m._forward_hooks.values()):
+            hook(m, (i,), o)
+
+    def conv_bn_act(seq, cin, cout, h, w, ho, wo, B):
+        fire(seq[0], (B, cin, h, w), (B, cout, ho, wo))
+        fire(seq[1], (B, cout, ho, wo), (B, cout, ho, wo))
+        fire(seq[2], (B, cout, ho, wo), (B, cout, ho, wo))
+        fire(seq, (B, cin, h, w), (B, cout, ho, wo))
+
+    B, _, H, W = x.shape
+    h, w = (H + 1) // 2, (W + 1) // 2
+    conv_bn_act(feats[0], 3, eng.stem.C, H, W, h, w, B)
+    for p in eng.blocks:
+        ho, wo = ((h + 1) // 2, (w + 1) // 2) if p.stride == 2 else (h, w)
+        for op, br in zip(p.mod.ops, p.branches):
+            d = 0
+            if p.expand:
+                conv_bn_act(op[0], p.inp, br.h, h, w, h, w, B)
+                d = 1
+            conv_bn_act(op[d], br.h, br.h, h, w, ho, wo, B)
+            fire(op[d + 1], (B, br.h, ho, wo), (B, p.oup, ho, wo))
+            fire(op, (B, p.inp, h, w), (B, p.oup, ho, wo))
+        fire(p.mod.ops, (B, p.inp, h, w), (B, p.oup, ho, wo))
+        fire(p.mod.pw_bn, (B, p.oup, ho, wo), (B, p.oup, ho, wo))
+        fire(p.mod, (B, p.inp, h, w), (B, p.oup, ho, wo))
+        h, w = ho, wo
+    hd = eng.head
+    conv_bn_act(feats[-2], hd.cin, hd.C, h, w, h, w, B)
+    fire(feats[-1], (B, hd.C, h, w), (B, hd.C, 1, 1))
+    fire(model.features, (B, 3, H, W), (B, hd.C, 1, 1))
+    fire(model.classifier[0], (B, hd.C), (B, hd.C))
+    fire(model.classifier[1], (B, hd.C), (B, hd.NC))
+    fire(model.classifier, (B, hd.C), (B, hd.NC))

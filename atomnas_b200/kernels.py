@@ -58,9 +58,11 @@ def pw_wgrad(p1, q, partials, Mrows, Cbig, Csmall, *, ldp1=None, ldq=None, p2=No
     return a.splits
 
 
-def wgrad_reduce(partials, splits, Cbig, Csmall, dst, sb, ss):
-    L.check(L.lib().an_wgrad_reduce(_c(partials), splits, Cbig, Csmall, _c(dst), sb, ss,
-                                    L.stream_ptr()), "an_wgrad_reduce")
+def wgrad_reduce(partials, splits, Cbig, Csmall, dst, sb, ss, row0=0, nrows=None, ncols=None):
+    nrows = Cbig - row0 if nrows is None else nrows
+    ncols = Csmall if ncols is None else ncols
+    L.check(L.lib().an_wgrad_reduce(_c(partials), splits, Cbig, Csmall, row0, nrows, ncols, _c(dst),
+                                    sb, ss, L.stream_ptr()), "an_wgrad_reduce")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -224,3 +226,19 @@ def refresh_weights(table, n_entries, total_tiles, src, dst16, dst32):
 def gather_rows(src, idx, n_out, inner, dst):
     L.check(L.lib().an_gather_rows(_c(src), _c(idx), n_out, inner, _c(dst), L.stream_ptr()),
             "an_gather_rows")
+
+
+def bn_eval_coeffs(gamma, beta, rm, rv, eps, C, scale, shift):
+    L.check(L.lib().an_bn_eval_coeffs(_c(gamma), _c(beta), _c(rm), _c(rv), eps, C, _c(scale),
+                                      _c(shift), L.stream_ptr()), "an_bn_eval_coeffs")
+
+
+def act_bwd_reduce(dy, x, scale, shift, mean, rstd, act, g, part, M, C, *, ldy, ldx, ldg):
+    L.check(L.lib().an_act_bwd_reduce(_c(dy), ldy, _c(x), ldx, _c(scale), _c(shift), _c(mean),
+                                      _c(rstd), act, _c(g), ldg, M, C, _c(part), L.stream_ptr()),
+            "an_act_bwd_reduce")
+
+
+def sum_rows(part, rows, row_stride, n, dst):
+    L.check(L.lib().an_sum_rows(_c(part), rows, row_stride, n, _c(dst), L.stream_ptr()),
+            "an_sum_rows")

@@ -1,0 +1,137 @@
+"""Fused training step: the public fast path of the package.
+
+One call = train.py:174-236 of the reference for one batch: forward, label-smoothed CE, backward,
+(bucketed NCCL all-reduce of the gradient arena overlapped with backward), RMSprop with the
+analytic L2 / L1 terms, EMA of parameters and BN running statistics, refresh of the bf16 weight
+copies -- with no per-parameter Python loop and no host synchronisation.
+
+    trainer = Trainer(model, lr=0.128, weight_decay=1e-5, ema_decay=0.9999 ** 0.5)
+    loss = trainer.step_host(images_pinned, labels_pinned)     # H2D + step; device scalar
+
+The drop-in route (reference train.py + utils.rmsprop.RMSprop + ExponentialMovingAverage) uses
+the same engine through atomnas_b200.rmsprop / atomnas_b200.optim instead.
+"""
+import torch
+import torch.distributed as dist
+
+from . import engine as E
+from . import kernels as K
+
+
+class Trainer(object):
+
+    def __init__(self, model, lr, alpha=0.9, momentum=0.9, eps=1e-3, eps_inside_sqrt=True,
+                 weight_decay=1e-5, label_smoothing=0.1, ema_decay=None, prune_penalties=None,
+                 bucket_bytes=8 << 20, use_cuda_graph=False):
+        self.model = model
+        self.eng = E.get_engine(model)
+        if not self.eng.is_net:
+            raise ValueError("Trainer needs a whole network")
+        eng = self.eng
+        self.lr, self.alpha, self.momentum, self.eps = lr, alpha, momentum, eps
+        self.eps_inside_sqrt = eps_inside_sqrt
+        self.weight_decay, self.label_smoothing = weight_decay, label_smoothing
+        self.ema_decay = ema_decay
+        self.sq = torch.zeros_like(eng.P)
+        self.buf = torch.zeros_like(eng.P)
+        self.ema_P = eng.P.clone() if ema_decay else None
+        self.ema_S = eng.S.clone() if ema_decay else None
+        if prune_penalties:
+            eng.set_l1_penalties(prune_penalties, dict(model.named_parameters()))
+        self.num_updates = 0
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.bucket_elems = max(1, bucket_bytes // 4)
+        self._handles = []
+        self._pending_hi = None
+        self._x_dev = None
+        self._y_dev = None
+        self.use_cuda_graph = use_cuda_graph and self.world == 1
+        self._graph = None
+        self._static = None
+
+    # ---- gradient all-reduce, bucketed in reverse arena order as backward releases ranges --------
+    def _grad_ready(self, offset):
+        if self.world == 1:
+            return
+        if self._pending_hi is None:
+            self._pending_hi = self.eng.n_params
+        if self._pending_hi - offset >= self.bucket_elems or offset == 0:
+            seg = self.eng.G[offset:self._pending_hi]
+            self._handles.append(dist.all_reduce(seg, async_op=True))
+            self._pending_hi = offset
+
+    def _finish_allreduce(self):
+        for h in self._handles:
+            h.wait()
+        self._handles = []
+        self._pending_hi = None
+
+    # ---- one step on device tensors ---------------------------------------------------------------
+    def _step_impl(self, x, target, rho, lr):
+        eng = self.eng
+        self.num_updates += 1
+        eng.forward(x, True, True, seed=self.num_updates)
+        loss = eng.loss_and_dlogits(target, self.label_smoothing, 1.0)
+        eng.backward(None, grad_ready=self._grad_ready)
+        self._finish_allreduce()
+        d = 0.0
+        ema = None
+        if self.ema_decay:
+            d = min(self.ema_decay, (1.0 + self.num_updates) / (10.0 + self.num_updates))
+            ema = self.ema_P
+        K.rmsprop_ema_step(eng.P, eng.G, self.sq, self.buf, ema, eng.wd_flag, eng.l1_pen, eng.n_params, lr,
+                           self.alpha, self.momentum, self.eps, self.eps_inside_sqrt, 1.0 / self.world,
+                           self.weight_decay, rho, d)
+        if self.ema_decay:
+            K.ema_update(self.ema_S, eng.S, eng.S.numel(), d)
+        eng.refresh_weights(force=True)
+        return loss
+
+    def step(self, x, target, rho=0.0, lr=None):
+        """x: fp32 NCHW on the device, target: int64 labels.  Returns per-sample losses (device)."""
+        lr = self.lr if lr is None else lr
+        if not self.use_cuda_graph:
+            return self._step_impl(x, target, rho, lr)
+        return self._step_graphed(x, target, rho, lr)
+
+    def _step_graphed(self, x, target, rho, lr):
+        """Whole step replayed from a CUDA graph (launch-bound inner loop; hyper-parameters are
+        baked at capture time, so the graph is re-captured when lr / rho change)."""
+        key = (tuple(x.shape), float(rho), float(lr))
+        if self._graph is None or self._static[2] != key:
+            sx, sy = x.clone(), target.clone()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):                         # warm-up outside capture
+                    self._step_impl(sx, sy, rho, lr)
+            torch.cuda.current_stream().wait_stream(side)
+            self._graph = torch.cuda.CUDAGraph()
+            n0 = self.num_updates
+            with torch.cuda.graph(self._graph):
+                out = self._step_impl(sx, sy, rho, lr)
+            self.num_updates = n0 + 1
+            self._static = (sx, sy, key, out)
+            return out
+        sx, sy, _, out = self._static
+        sx.copy_(x, non_blocking=True)
+        sy.copy_(target, non_blocking=True)
+        self.num_updates += 1
+        self._graph.replay()
+        return out
+
+    def step_host(self, x_host, y_host, rho=0.0, lr=None):
+        """End-to-end step from (pinned) host buffers: H2D copies, the step, mean loss (device)."""
+        if self._x_dev is None or self._x_dev.shape != x_host.shape:
+            self._x_dev = torch.empty(x_host.shape, device=self.eng.dev, dtype=torch.float32)
+            self._y_dev = torch.empty(y_host.shape, device=self.eng.dev, dtype=torch.int64)
+        self._x_dev.copy_(x_host, non_blocking=True)
+        self._y_dev.copy_(y_host, non_blocking=True)
+        return self.step(self._x_dev, self._y_dev, rho, lr).mean()
+
+    def reg_losses(self, rho):
+        """(l2, l1) regularisation loss values for logging (train.py:203-208)."""
+        part = torch.zeros(128, 2, device=self.eng.dev)
+        K.reg_losses(self.eng.P, self.eng.wd_flag, self.eng.l1_pen, self.eng.n_params, part)
+        s = part.sum(0)
+        return 0.5 * self.weight_decay * s[0], rho * s[1]

@@ -90,8 +90,9 @@ typedef struct {
 
 int an_pw_wgrad_splits(int Mrows, int Cbig, int Csmall);
 int an_pw_wgrad(const an_pw_wgrad_args* args, void* stream);
-int an_wgrad_reduce(const float* partials, int splits, int Cbig, int Csmall, float* dst,
-                    long long dst_sb, long long dst_ss, void* stream);
+/* dst[(cb-row0)*dst_sb + cs*dst_ss] = sum_s partials[s][cb][cs], cb in [row0,row0+nrows), cs < ncols */
+int an_wgrad_reduce(const float* partials, int splits, int Cbig, int Csmall, int row0, int nrows,
+                    int ncols, float* dst, long long dst_sb, long long dst_ss, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Depthwise k x k convolution (k = 3, 5, 7; stride 1, 2; pad (k-1)/2), NHWC bf16, CUDA cores.
@@ -153,6 +154,15 @@ int an_bn_bwd_finalize(const float* stats_part, int rows, int C, double count, c
 int an_affine_act(const void* x1, long long ld1, const void* x2, long long ld2, const float* a1,
                   const float* a2, const float* a3, int act, void* out, long long ldo, long long M,
                   int C, void* stream);
+int an_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean,
+                      const float* running_var, float eps, int C, float* scale, float* shift,
+                      void* stream);
+/* g = dy*act'(scale*x+shift) + partials of sum g, sum g*xhat (same row count as an_col_reduce) */
+int an_act_bwd_reduce(const void* dy, long long ldy, const void* x, long long ldx, const float* scale,
+                      const float* shift, const float* mean, const float* rstd, int act, void* g,
+                      long long ldg, long long M, int C, float* stats_part, void* stream);
+int an_sum_rows(const float* part, int rows, long long row_stride, long long n, float* dst,
+                void* stream);
 int an_col_reduce_rows(long long M, int C);
 int an_col_reduce(const void* g, long long ldg, const void* x, long long ldx, const float* mean,
                   const float* rstd, long long M, int C, float* stats_part, void* stream);
@@ -184,13 +194,13 @@ int an_f32_to_bf16(const float* src, long long lds, void* dst, long long ldd, lo
                    int cols, int cols_pad, void* stream);
 
 /* ------------------------------------------------------------------------------------------
- * Fused optimizer over flat arenas (every tensor starts at a multiple of 256 elements; wd_flag /
- * l1_pen hold one value per 256-element chunk):
+ * Fused optimizer over flat arenas (wd_flag / l1_pen are per-element arrays parallel to the arena;
+ * wd_flag < 0 marks frozen padding elements):
  *   g' = g*grad_scale + weight_decay*wd_flag*p + rho*l1_pen*sign(p)
  *   RMSprop (utils/rmsprop.py:100-130), then ema = d*ema + (1-d)*p (utils/optim.py:64-65).
  * an_refresh_weights re-materialises the kernel-layout weight copies (bf16 [N,K], bf16 [K,N]
  * transposes for dgrad, fp32 tap-major depthwise) from the fp32 master arena via a table of
- * 8 x int64 entries {src_off, dst_off, rows, cols, dst_ld, transpose, dst_f32, first_tile}.
+ * 9 x int64 entries {src_ld, src_off, dst_off, rows, cols, dst_ld, transpose, dst_f32, first_tile}.
  * an_gather_rows is the bit-exact `rhs[mask]` of models/compress_utils.py:31-37.
  * ------------------------------------------------------------------------------------------ */
 int an_rmsprop_ema_step(float* p, const float* g, float* sq, float* buf, float* ema,

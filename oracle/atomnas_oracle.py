@@ -248,6 +248,73 @@ def forward(spec, st, x, training=True, dropout_mask=None):
 
 
 # ------------------------------------------------------------------------------------------------
+# forward with the product's bf16 storage points (still CPU fp32 arithmetic)
+# ------------------------------------------------------------------------------------------------
+class _Round(torch.autograd.Function):
+    """Round to bf16 in forward and/or backward (straight-through)."""
+
+    @staticmethod
+    def forward(ctx, x, fwd, bwd):
+        ctx.bwd = bwd
+        return x.to(torch.bfloat16).to(x.dtype) if fwd else x.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        return (g.to(torch.bfloat16).to(g.dtype) if ctx.bwd else g), None, None
+
+
+def _q2(x): return _Round.apply(x, True, True)       # tensor stored in bf16, so is its gradient
+def _qf(x): return _Round.apply(x, True, False)      # operand rounded on the fly (GEMM A / dw input)
+def _qb(x): return _Round.apply(x, False, True)      # only the gradient is stored in bf16
+def _qw(w): return w + (w.to(torch.bfloat16).to(w.dtype) - w).detach()   # bf16 weight copy
+
+
+def block_forward_bf16_points(spec, st, b, y, training=True):
+    """One InvertedResidualChannels block with the engine's bf16 storage points; `y` is the
+    (bf16-valued) block input."""
+    a = spec.active_fn
+    if len(b.channels) == 0:
+        return y
+    tmp = 0
+    for j, (h, k) in enumerate(zip(b.channels, b.kernel_sizes)):
+        base = "%s.ops.%d" % (b.name, j)
+        t, d = y, 0
+        if b.expand:
+            t = _q2(F.conv2d(y, _qw(st[base + ".0.0.weight"])))
+            t = _qf(act(_qb(_bn(spec, st, base + ".0.1", t, training)), a))
+            d = 1
+        t = _q2(F.conv2d(t, st["%s.%d.0.weight" % (base, d)], None, b.stride, (k - 1) // 2, 1, h))
+        t = _qf(act(_qb(_bn(spec, st, "%s.%d.1" % (base, d), t, training)), a))
+        tmp = tmp + F.conv2d(t, _qw(st["%s.%d.weight" % (base, d + 1)]))
+    tmp = _bn(spec, st, b.name + ".pw_bn", _q2(tmp), training)
+    return _q2(y + tmp) if (b.stride == 1 and b.inp == b.oup) else _q2(tmp)
+
+
+def forward_bf16_points(spec, st, x, training=True):
+    """Same network as `forward`, in fp32 arithmetic, but rounding to bf16 exactly where the B200
+    engine stores bf16 (DESIGN.md 'data layout'): raw conv outputs and their gradients, the
+    activated operands fed to the next conv, block outputs, gradients w.r.t. BN outputs, and the
+    bf16 copies of the 1x1 / classifier weights.  Differences to the engine that remain are fp32
+    accumulation order and fast-math exp -- so this is the tight parity target, while `forward`
+    (pure fp32 == the reference) measures the bf16 error itself."""
+    a = spec.active_fn
+
+    def bn_act(name, t, fwd_round):
+        t = act(_qb(_bn(spec, st, name, t, training)), a)
+        return _qf(t) if fwd_round else t
+
+    s = _q2(F.conv2d(x, st["features.0.0.weight"], None, 2, 1))
+    y = _q2(bn_act("features.0.1", s, False))
+    for b in spec.blocks:
+        y = block_forward_bf16_points(spec, st, b, y, training)
+    hn = "features.%d" % spec.head_index
+    t = _q2(F.conv2d(y, _qw(st[hn + ".0.weight"])))
+    t = bn_act(hn + ".1", t, False)
+    t = _q2(F.avg_pool2d(t, spec.input_size // 32).squeeze(3).squeeze(2))
+    return _qb(F.linear(t, _qw(st["classifier.1.weight"]), st["classifier.1.bias"]))
+
+
+# ------------------------------------------------------------------------------------------------
 # losses
 # ------------------------------------------------------------------------------------------------
 def cross_entropy_label_smooth(logits, target, num_classes, eps):

@@ -255,14 +255,17 @@ def test_rmsprop_ema_matches_oracle():
     g = torch.randn(n) * 0.1
     sq, buf = torch.rand(n) * 0.01, torch.randn(n) * 0.1
     ema = p.clone()
-    wd_flag = (torch.arange(40) % 2).float()
-    l1_pen = ((torch.arange(40) % 3) == 0).float() * 2.5
+    wd_flag = (torch.arange(40) % 2).float().repeat_interleave(256)
+    l1_pen = (((torch.arange(40) % 3) == 0).float() * 2.5).repeat_interleave(256)
+    wd_flag[7] = -1.0      # frozen padding element
     lr, wd, rho, decay, world = 0.128, 1e-5, 1e-4, 0.99995, 8
     d = [t.clone().to(DEV) for t in (p, g, sq, buf, ema, wd_flag, l1_pen)]
     K.rmsprop_ema_step(d[0], d[1], d[2], d[3], d[4], d[5], d[6], n, lr, 0.9, 0.9, 1e-3, True,
                        1.0 / world, wd, rho, decay)
-    gg = g / world + wd * wd_flag.repeat_interleave(256) * p + rho * l1_pen.repeat_interleave(256) * torch.sign(p)
+    gg = g / world + wd * wd_flag * p + rho * l1_pen * torch.sign(p)
+    p7, s7, b7 = p[7].clone(), sq[7].clone(), buf[7].clone()
     O.rmsprop_step(p, gg, sq, buf, lr)
+    p[7], sq[7], buf[7] = p7, s7, b7
     O.ema_update(ema, p, decay)
     torch.testing.assert_close(d[0].cpu(), p, rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(d[2].cpu(), sq, rtol=1e-5, atol=1e-9)
@@ -271,8 +274,8 @@ def test_rmsprop_ema_matches_oracle():
     part = torch.zeros(128, 2, device=DEV)
     K.reg_losses(d[0], d[5], d[6], n, part)
     s = part.sum(0).cpu()
-    torch.testing.assert_close(s[0], (wd_flag.repeat_interleave(256) * p * p).sum(), rtol=1e-4, atol=1e-4)
-    torch.testing.assert_close(s[1], (l1_pen.repeat_interleave(256) * p.abs()).sum(), rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(s[0], (wd_flag.clamp(min=0) * p * p).sum(), rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(s[1], (l1_pen * p.abs()).sum(), rtol=1e-4, atol=1e-4)
 
 
 def test_refresh_and_gather_bit_exact():
@@ -283,7 +286,7 @@ def test_refresh_and_gather_bit_exact():
     ents = [(100, 0, 24, 40, 48, 0, 0), (100, 2000, 24, 40, 24, 1, 0), (1500, 10, 16, 9, 16, 1, 1)]
     table, blk = [], 0
     for so, do, r, c, ld, tr, f32 in ents:
-        table.append([so, do, r, c, ld, tr, f32, blk])
+        table.append([c, so, do, r, c, ld, tr, f32, blk])
         blk += ((r + 31) // 32) * ((c + 31) // 32)
     tt = torch.tensor(table, dtype=torch.int64, device=DEV)
     d16 = torch.zeros(4000, device=DEV, dtype=torch.bfloat16)

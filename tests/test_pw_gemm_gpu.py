@@ -147,3 +147,7 @@ def test_pw_wgrad(Mr, Cb, Cs, p_mode):
     tol = 2e-3 * ref.abs().max().item() + 1e-3
     assert (out - ref).abs().max().item() <= tol
     assert torch.equal(out_t, out.t())
+    if Cs > 8:
+        sub = torch.zeros(Cs - 8, 40, device=dev)       # rows [16,56) of the big side, transposed
+        K.wgrad_reduce(partials, splits, Cb, Cs, sub, 1, 40, row0=16, nrows=40, ncols=Cs - 8)
+        assert torch.equal(sub, out[16:56, :Cs - 8].t())
