@@ -63,6 +63,7 @@ SIGNATURES = {
     "an_last_error": (ctypes.c_char_p, []),
     "an_version": (c_int, []),
     "an_sm_count": (c_int, []),
+    "an_launch_count": (c_ll, []),
     "an_pw_gemm": (c_int, [ctypes.POINTER(PwGemmArgs), c_vp]),
     "an_pw_gemm_stats_rows": (c_int, [c_int, c_int]),
     "an_pw_wgrad_splits": (c_int, [c_int, c_int, c_int]),
@@ -82,7 +83,7 @@ SIGNATURES = {
     "an_bn_finalize": (c_int, [c_fp, c_int, c_int, c_d, c_fp, c_fp, c_fp, c_fp, c_f, c_f, c_fp,
                                c_fp, c_fp, c_fp, c_vp]),
     "an_bn_bwd_finalize": (c_int, [c_fp, c_int, c_int, c_d, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp,
-                                   c_fp, c_fp, c_vp]),
+                                   c_fp, c_fp, c_int, c_vp]),
     "an_affine_act": (c_int, [c_vp, c_ll, c_vp, c_ll, c_fp, c_fp, c_fp, c_int, c_vp, c_ll, c_ll,
                               c_int, c_vp]),
     "an_col_reduce_rows": (c_int, [c_ll, c_int]),
@@ -93,27 +94,77 @@ SIGNATURES = {
                               c_int, c_int, c_int, c_vp]),
     "an_stem_wgrad_rows": (c_int, [c_int, c_int, c_int]),
     "an_pool_fwd": (c_int, [c_vp, c_ll, c_fp, c_fp, c_int, c_vp, c_ll, c_int, c_int, c_int, c_f,
-                            c_ull, c_vp]),
+                            c_ull, c_vp, c_vp]),
     "an_pool_bwd": (c_int, [c_vp, c_ll, c_vp, c_ll, c_fp, c_fp, c_fp, c_fp, c_int, c_vp, c_ll,
-                            c_fp, c_int, c_int, c_int, c_f, c_ull, c_vp]),
+                            c_fp, c_int, c_int, c_int, c_f, c_ull, c_vp, c_vp]),
     "an_pool_bwd_stats_rows": (c_int, [c_int]),
     "an_ce_loss": (c_int, [c_fp, c_ll, c_vp, c_int, c_int, c_f, c_f, c_fp, c_vp, c_ll, c_int,
                            c_vp]),
     "an_f32_to_bf16": (c_int, [c_fp, c_ll, c_vp, c_ll, c_ll, c_int, c_int, c_vp]),
     "an_rmsprop_ema_step": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_ll, c_f, c_f, c_f,
-                                    c_f, c_int, c_f, c_f, c_f, c_f, c_vp]),
-    "an_ema_update": (c_int, [c_fp, c_fp, c_ll, c_f, c_vp]),
+                                    c_f, c_int, c_f, c_f, c_f, c_f, c_fp, c_vp]),
+    "an_ema_update": (c_int, [c_fp, c_fp, c_ll, c_f, c_fp, c_vp]),
     "an_reg_losses": (c_int, [c_fp, c_fp, c_fp, c_ll, c_fp, c_vp]),
     "an_refresh_weights": (c_int, [c_vp, c_int, c_ll, c_fp, c_vp, c_fp, c_vp]),
     "an_gather_rows": (c_int, [c_fp, c_vp, c_ll, c_ll, c_fp, c_vp]),
 }
 
 _lib = None
+_profiler = None
+TAG = [""]            # set by the engine at stage boundaries; only read while profiling
+
+
+class _Profiler(object):
+    """Brackets every kernel-launching entry point with CUDA events on the launching stream
+    (bench.py roofline measurement; serialises nothing, but adds two event records per call)."""
+
+    def __init__(self, handle):
+        self._h = handle
+        self.records = []
+
+    def __getattr__(self, name):
+        fn = getattr(self._h, name)
+        if not name.startswith("an_") or fn.restype is not c_int or name.endswith(("_rows", "_splits")) \
+                or name in ("an_version", "an_sm_count"):
+            return fn
+
+        def timed(*args):
+            s = torch.cuda.Event(enable_timing=True)
+            e = torch.cuda.Event(enable_timing=True)
+            s.record()
+            r = fn(*args)
+            e.record()
+            self.records.append((name, TAG[0], s, e))
+            return r
+
+        return timed
+
+
+def start_profile():
+    global _profiler
+    lib()
+    _profiler = _Profiler(_lib)
+
+
+def stop_profile():
+    """Return {(entry point, tag): [calls, total ms]} since start_profile()."""
+    global _profiler
+    torch.cuda.synchronize()
+    out = {}
+    for name, tag, s, e in _profiler.records:
+        k = (name, tag)
+        c = out.setdefault(k, [0, 0.0])
+        c[0] += 1
+        c[1] += s.elapsed_time(e)
+    _profiler = None
+    return out
 
 
 def lib():
     """Load (once) and return the shared library; raise loudly if it was not built."""
     global _lib
+    if _profiler is not None:
+        return _profiler
     if _lib is None:
         if not os.path.exists(LIB_PATH):
             raise RuntimeError(

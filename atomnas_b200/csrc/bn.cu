@@ -12,18 +12,45 @@
 
 namespace an {
 
+// Sum the per-CTA partials [rows][2][C] of channel c: 8 row lanes per channel (fixed order:
+// lane l takes rows l, l+8, ...; lanes combined 0..7), fp64.  Block = 32 channels x 8 lanes.
+constexpr int kFinLanes = 8;
+__device__ __forceinline__ bool reduce_partials(const float* __restrict__ part, int rows, int C,
+                                                double* s1, double* s2, int* c_out) {
+  __shared__ double sh[2][kFinLanes][32];
+  const int lc = threadIdx.x % 32, lr = threadIdx.x / 32;
+  const int c = blockIdx.x * 32 + lc;
+  double a = 0.0, b = 0.0;
+  if (c < C) {
+    for (int r = lr; r < rows; r += kFinLanes) {
+      a += static_cast<double>(part[(static_cast<long long>(r) * 2 + 0) * C + c]);
+      b += static_cast<double>(part[(static_cast<long long>(r) * 2 + 1) * C + c]);
+    }
+  }
+  sh[0][lr][lc] = a;
+  sh[1][lr][lc] = b;
+  __syncthreads();
+  if (lr != 0 || c >= C) return false;
+  a = 0.0;
+  b = 0.0;
+  for (int l = 0; l < kFinLanes; ++l) {
+    a += sh[0][l][lc];
+    b += sh[1][l][lc];
+  }
+  *s1 = a;
+  *s2 = b;
+  *c_out = c;
+  return true;
+}
+
 __global__ void bn_finalize_kernel(const float* __restrict__ part, int rows, int C, double count,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* running_mean, float* running_var, float momentum,
                                    float eps, float* mean_out, float* rstd_out, float* scale_out,
                                    float* shift_out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s1 = 0.0, s2 = 0.0;
-  for (int r = 0; r < rows; ++r) {
-    s1 += static_cast<double>(part[(static_cast<long long>(r) * 2 + 0) * C + c]);
-    s2 += static_cast<double>(part[(static_cast<long long>(r) * 2 + 1) * C + c]);
-  }
+  double s1, s2;
+  int c;
+  if (!reduce_partials(part, rows, C, &s1, &s2, &c)) return;
   const double mean = s1 / count;
   double var = s2 / count - mean * mean;
   if (var < 0.0) var = 0.0;
@@ -48,14 +75,11 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int rows,
                                        double count, const float* __restrict__ gamma,
                                        const float* __restrict__ mean,
                                        const float* __restrict__ rstd, float* dgamma, float* dbeta,
-                                       float* ca, float* cb, float* cc) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s1 = 0.0, s2 = 0.0;
-  for (int r = 0; r < rows; ++r) {
-    s1 += static_cast<double>(part[(static_cast<long long>(r) * 2 + 0) * C + c]);
-    s2 += static_cast<double>(part[(static_cast<long long>(r) * 2 + 1) * C + c]);
-  }
+                                       float* ca, float* cb, float* cc, int raw_second) {
+  double s1, s2;
+  int c;
+  if (!reduce_partials(part, rows, C, &s1, &s2, &c)) return;
+  if (raw_second) s2 = static_cast<double>(rstd[c]) * (s2 - static_cast<double>(mean[c]) * s1);   // sum g*x -> sum g*xhat
   if (dbeta) dbeta[c] = static_cast<float>(s1);
   if (dgamma) dgamma[c] = static_cast<float>(s2);
   const float g = gamma ? gamma[c] : 1.f;
@@ -262,7 +286,7 @@ extern "C" int an_bn_finalize(const float* stats_part, int rows, int C, double c
                               float* running_var, float momentum, float eps, float* mean,
                               float* rstd, float* scale, float* shift, void* stream) {
   AN_REQUIRE(stats_part && rows > 0 && C > 0 && mean && rstd && scale && shift, "an_bn_finalize: bad arguments");
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  bn_finalize_kernel<<<(C + 31) / 32, 32 * kFinLanes, 0, static_cast<cudaStream_t>(stream)>>>(
       stats_part, rows, C, count, gamma, beta, running_mean, running_var, momentum, eps, mean, rstd,
       scale, shift);
   AN_CHECK_LAUNCH();
@@ -272,10 +296,10 @@ extern "C" int an_bn_finalize(const float* stats_part, int rows, int C, double c
 extern "C" int an_bn_bwd_finalize(const float* stats_part, int rows, int C, double count,
                                   const float* gamma, const float* mean, const float* rstd,
                                   float* dgamma, float* dbeta, float* ca, float* cb, float* cc,
-                                  void* stream) {
+                                  int raw_second, void* stream) {
   AN_REQUIRE(stats_part && rows > 0 && C > 0 && mean && rstd && ca && cb && cc, "an_bn_bwd_finalize: bad arguments");
-  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      stats_part, rows, C, count, gamma, mean, rstd, dgamma, dbeta, ca, cb, cc);
+  bn_bwd_finalize_kernel<<<(C + 31) / 32, 32 * kFinLanes, 0, static_cast<cudaStream_t>(stream)>>>(
+      stats_part, rows, C, count, gamma, mean, rstd, dgamma, dbeta, ca, cb, cc, raw_second);
   AN_CHECK_LAUNCH();
   return 0;
 }

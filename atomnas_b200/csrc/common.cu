@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include "../../include/atomnas_b200.h"
 
+#include <atomic>
 #include <mutex>
 #include <stdarg.h>
 #include <string.h>
@@ -17,6 +18,9 @@ void set_last_error(const char* fmt, ...) {
   va_end(ap);
 }
 const char* get_last_error() { return g_err; }
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int sm_count() {
   static int cached = 0;
@@ -77,3 +81,4 @@ int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_
 extern "C" const char* an_last_error(void) { return an::get_last_error(); }
 extern "C" int an_version(void) { return 100; }
 extern "C" int an_sm_count(void) { return an::sm_count(); }
+extern "C" long long an_launch_count(void) { return an::g_launches.load(); }

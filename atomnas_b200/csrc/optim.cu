@@ -20,7 +20,12 @@ __global__ void rmsprop_ema_kernel(float* __restrict__ p, const float* __restric
                                    const float* __restrict__ l1_pen, long long n, float lr,
                                    float alpha, float momentum, float eps, int eps_inside_sqrt,
                                    float grad_scale, float weight_decay, float rho,
-                                   float ema_decay) {
+                                   float ema_decay, const float* __restrict__ hp) {
+  if (hp != nullptr) {          // per-step values from device memory (CUDA-graph replay)
+    lr = hp[0];
+    rho = hp[1];
+    ema_decay = hp[2];
+  }
   const long long i4 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 4;
   if (i4 >= n) return;
   const float4 wf = *reinterpret_cast<const float4*>(wd_flag + i4);
@@ -60,7 +65,9 @@ __global__ void rmsprop_ema_kernel(float* __restrict__ p, const float* __restric
   }
 }
 
-__global__ void ema_kernel(float* __restrict__ ema, const float* __restrict__ x, long long n, float decay) {
+__global__ void ema_kernel(float* __restrict__ ema, const float* __restrict__ x, long long n, float decay,
+                           const float* __restrict__ hp) {
+  if (hp != nullptr) decay = hp[2];
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i < n) ema[i] = ema[i] * decay + (1.f - decay) * x[i];
 }
@@ -149,20 +156,21 @@ extern "C" int an_rmsprop_ema_step(float* p, const float* g, float* sq, float* b
                                    const float* wd_flag, const float* l1_pen, long long n, float lr,
                                    float alpha, float momentum, float eps, int eps_inside_sqrt,
                                    float grad_scale, float weight_decay, float rho, float ema_decay,
-                                   void* stream) {
+                                   const float* hparams_dev, void* stream) {
   AN_REQUIRE(p && g && sq && wd_flag && l1_pen && n > 0 && n % 4 == 0, "an_rmsprop_ema_step: arena must be a multiple of 4 elements");
   AN_REQUIRE(momentum <= 0.f || buf, "an_rmsprop_ema_step: momentum needs a buffer");
   const long long threads = n / 4;
   rmsprop_ema_kernel<<<static_cast<int>((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       p, g, sq, buf, ema, wd_flag, l1_pen, n, lr, alpha, momentum, eps, eps_inside_sqrt, grad_scale, weight_decay,
-      rho, ema_decay);
+      rho, ema_decay, hparams_dev);
   AN_CHECK_LAUNCH();
   return 0;
 }
 
-extern "C" int an_ema_update(float* ema, const float* x, long long n, float decay, void* stream) {
+extern "C" int an_ema_update(float* ema, const float* x, long long n, float decay, const float* hparams_dev,
+                             void* stream) {
   AN_REQUIRE(ema && x && n > 0, "an_ema_update: bad arguments");
-  ema_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(ema, x, n, decay);
+  ema_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(ema, x, n, decay, hparams_dev);
   AN_CHECK_LAUNCH();
   return 0;
 }

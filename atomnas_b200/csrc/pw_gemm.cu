@@ -28,7 +28,7 @@ constexpr int kTileB = kMaxBN * kBK * 2;   // 16 KiB
 constexpr int kThreads = 320;
 constexpr int kMaxGroupCols = 1024;        // columns whose BN partials one CTA keeps in smem
 constexpr int kTmemCols = 256;             // 2 accumulator buffers x 128 columns
-constexpr int kAuxBytes = 256 + 4 * 2 * kMaxBN * 4 + 2 * kMaxGroupCols * 4;
+constexpr int kAuxBytes = 256 + 4 * 2 * kMaxBN * 4 + 2 * kMaxGroupCols * 4 + kMaxBN * 8;
 
 struct GemmDev {
   CUtensorMap tm_x1, tm_x2, tm_w;
@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_kernel(const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   float* stat_warp = reinterpret_cast<float*>(aux + 256);   // [4][2][kMaxBN]
   float* stat_acc = stat_warp + 4 * 2 * kMaxBN;             // [2][kMaxGroupCols]
+  float2* colpar = reinterpret_cast<float2*>(stat_acc + 2 * kMaxGroupCols);   // [kMaxBN]
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tm_x1);
@@ -103,7 +104,7 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_kernel(const __grid_const
       }
       for (int b = 0; b < 2; ++b) {
         mbar_init(&tfull[b], 1);
-        mbar_init(&tempty[b], 128);
+        mbar_init(&tempty[b], p.a_mode == 0 ? 256 : 128);
       }
       mbar_fence_init();
     }
@@ -167,43 +168,50 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_kernel(const __grid_const
           }
         }
     }
-  } else if (warp < 6) {
+  } else if (warp < 6 && p.a_mode != 0) {
     // ------------------------------------------------------------------ A-operand prologue
-    if (p.a_mode != 0) {
-      const int t = threadIdx.x - 64;
-      const int cp = t & 7, r0 = t >> 3;
-      const int cl = cp ^ (r0 & 7);            // logical 16B chunk held at physical chunk cp
-      uint32_t it = 0;
-      for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x)
-        for (int nt = nt_begin; nt < nt_end; ++nt)
-          for (int kb = 0; kb < kblocks; ++kb, ++it) {
-            const int s = it % S;
-            const uint32_t ph = (it / S) & 1;
-            const int kch = kb * kBK + cl * 8;
-            float c1[8], c2[8], c3[8];
-            load_coef8(p.a1, kch, p.K, c1, 0.f);
-            load_coef8(p.a3, kch, p.K, c3, 0.f);
-            if (p.a_mode == 2) load_coef8(p.a2, kch, p.K, c2, 0.f);
-            mbar_wait(&full[s], ph);
-            uint8_t* a = smem + s * stage_bytes + r0 * 128 + cp * 16;
+    const int t = threadIdx.x - 64;
+    const int cp = t & 7, r0 = t >> 3;
+    const int cl = cp ^ (r0 & 7);            // logical 16B chunk held at physical chunk cp
+    uint32_t it = 0;
+    for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x)
+      for (int nt = nt_begin; nt < nt_end; ++nt)
+        for (int kb = 0; kb < kblocks; ++kb, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1;
+          const int kch = kb * kBK + cl * 8;
+          float c1[8], c2[8], c3[8];
+          load_coef8(p.a1, kch, p.K, c1, 0.f);
+          load_coef8(p.a3, kch, p.K, c3, 0.f);
+          if (p.a_mode == 2) load_coef8(p.a2, kch, p.K, c2, 0.f);
+          mbar_wait(&full[s], ph);
+          uint8_t* a = smem + s * stage_bytes + r0 * 128 + cp * 16;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              uint4* ptr = reinterpret_cast<uint4*>(a + i * 16 * 128);
-              const uint4 v = *ptr;
-              uint4 w = make_uint4(0, 0, 0, 0);
-              if (p.a_mode == 2) w = *reinterpret_cast<const uint4*>(a + i * 16 * 128 + kTileA);
-              *ptr = transform_chunk(v, w, p.a_mode, p.a_act, c1, c2, c3);
-            }
-            fence_proxy_async_smem();
-            mbar_arrive(&xf[s]);
+          for (int i = 0; i < 8; ++i) {
+            uint4* ptr = reinterpret_cast<uint4*>(a + i * 16 * 128);
+            const uint4 v = *ptr;
+            uint4 w = make_uint4(0, 0, 0, 0);
+            if (p.a_mode == 2) w = *reinterpret_cast<const uint4*>(a + i * 16 * 128 + kTileA);
+            *ptr = transform_chunk(v, w, p.a_mode, p.a_act, c1, c2, c3);
           }
-    }
+          fence_proxy_async_smem();
+          mbar_arrive(&xf[s]);
+        }
   } else {
     // ------------------------------------------------------------------ epilogue
+    // Warps 6-9 always; warps 2-5 join when there is no operand prologue (a_mode 0: exactly the
+    // output-heavy GEMMs -- expand forward, projection dgrad).  Each TMEM lane quarter is then
+    // served by two warps that split the tile's 16-column chunks.
+    const int nhalves = (p.a_mode == 0) ? 2 : 1;
+    const int half = (warp < 6) ? 1 : 0;
+    const int n_epi = 128 * nhalves;
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
     const int et = q * 32 + lane;              // row within the tile
+    const int ep_tid = half * 128 + et;
     const bool want_stats = p.stats_part != nullptr;
     const int nchunks = p.block_n / 16;
+    const int c_begin = (nhalves == 1) ? 0 : (half == 0 ? 0 : (nchunks + 1) / 2);
+    const int c_end = (nhalves == 1) ? nchunks : (half == 0 ? (nchunks + 1) / 2 : nchunks);
     uint32_t tc = 0;
     for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x)
       for (int nt = nt_begin; nt < nt_end; ++nt, ++tc) {
@@ -211,127 +219,137 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_kernel(const __grid_const
         const long long row = static_cast<long long>(mt) * kBM + et;
         const bool row_ok = row < p.M;
         const int ncol0 = nt * p.block_n;
+        if (p.epi_mode == 1) {                 // per-column (scale, shift) of this tile -> smem
+          for (int c = ep_tid; c < p.block_n; c += n_epi) {
+            const int col = ncol0 + c;
+            colpar[c] = (col < p.N) ? make_float2(__ldg(p.r_scale + col), __ldg(p.r_shift + col))
+                                    : make_float2(0.f, 0.f);
+          }
+        }
         uint4 rr[16];
         if (p.epi_mode != 0) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int col = ncol0 + j * 8;
-            rr[j] = make_uint4(0, 0, 0, 0);
-            if (p.r != nullptr && j < 2 * nchunks && row_ok && col < p.N)
-              rr[j] = ldg_nc_v4(p.r + row * p.ldr + col);
+          for (int jj = 0; jj < 16; ++jj) {     // rr[k] = 8 columns starting at chunk c_begin, +8k
+            const int col = ncol0 + c_begin * 16 + jj * 8;
+            rr[jj] = make_uint4(0, 0, 0, 0);
+            if (p.r != nullptr && c_begin * 2 + jj < 2 * c_end && row_ok && col < p.N)
+              rr[jj] = ldg_nc_v4(p.r + row * p.ldr + col);
           }
         }
+        if (p.epi_mode == 1) named_bar_sync(1, n_epi);
         mbar_wait(&tfull[buf], tph);
         tc_fence_after();
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kMaxBN;
+
+        auto process = [&](float* v, int j, const uint4& ra, const uint4& rb) {
+          const int col0 = ncol0 + j * 16;
+          float s1[16], s2[16];
+          if (p.epi_mode == 0) {
+            if (p.bias != nullptr) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (j < nchunks) {
-            float v[16];
-            tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kMaxBN + j * 16, v);
-            const int col0 = ncol0 + j * 16;
-            float s1[16], s2[16];
-            if (p.epi_mode == 0) {
-              if (p.bias != nullptr) {
+              for (int c = 0; c < 16; ++c)
+                if (col0 + c < p.N) v[c] += __ldg(p.bias + col0 + c);
+            }
+            if (!p.y_is_f32) {
 #pragma unroll
-                for (int c = 0; c < 16; ++c)
-                  if (col0 + c < p.N) v[c] += __ldg(p.bias + col0 + c);
-              }
-              if (!p.y_is_f32) {
+              for (int c = 0; c < 16; ++c) v[c] = round_bf16(v[c]);
+            }
 #pragma unroll
-                for (int c = 0; c < 16; ++c) v[c] = round_bf16(v[c]);
-              }
+            for (int c = 0; c < 16; ++c) {
+              const float x = (row_ok && col0 + c < p.N) ? v[c] : 0.f;
+              s1[c] = x;
+              s2[c] = x * x;
+            }
+          } else {
+            const uint32_t ri[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+            float rv[16];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              rv[2 * c] = bf16_lo(ri[c]);
+              rv[2 * c + 1] = bf16_hi(ri[c]);
+            }
+            if (p.epi_mode == 1) {
 #pragma unroll
               for (int c = 0; c < 16; ++c) {
-                const float x = (row_ok && col0 + c < p.N) ? v[c] : 0.f;
-                s1[c] = x;
-                s2[c] = x * x;
+                const float2 cpv = colpar[j * 16 + c];
+                const float pre = fmaf(cpv.x, rv[c], cpv.y);
+                const float g = (row_ok && col0 + c < p.N) ? round_bf16(v[c] * act_bwd(pre, p.r_act)) : 0.f;
+                v[c] = g;
+                s1[c] = g;
+                s2[c] = g * rv[c];           // raw second moment; the finalize kernel centres it
               }
             } else {
-              const uint32_t ri[8] = {rr[2 * j].x,     rr[2 * j].y,     rr[2 * j].z,
-                                      rr[2 * j].w,     rr[2 * j + 1].x, rr[2 * j + 1].y,
-                                      rr[2 * j + 1].z, rr[2 * j + 1].w};
-              float rv[16];
 #pragma unroll
-              for (int c = 0; c < 8; ++c) {
-                rv[2 * c] = bf16_lo(ri[c]);
-                rv[2 * c + 1] = bf16_hi(ri[c]);
-              }
-              if (p.epi_mode == 1) {
-#pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                  const int col = col0 + c;
-                  float g = 0.f, xh = 0.f;
-                  if (row_ok && col < p.N) {
-                    const float pre = fmaf(__ldg(p.r_scale + col), rv[c], __ldg(p.r_shift + col));
-                    g = round_bf16(v[c] * act_bwd(pre, p.r_act));
-                    xh = (rv[c] - __ldg(p.r_mean + col)) * __ldg(p.r_rstd + col);
-                  }
-                  v[c] = g;
-                  s1[c] = g;
-                  s2[c] = g * xh;
-                }
-              } else {
-#pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                  v[c] = round_bf16(v[c] + rv[c]);
-                  s1[c] = 0.f;
-                  s2[c] = 0.f;
-                }
+              for (int c = 0; c < 16; ++c) {
+                v[c] = round_bf16(v[c] + rv[c]);
+                s1[c] = 0.f;
+                s2[c] = 0.f;
               }
             }
-            // ---- store
-            if (row_ok) {
-              if (p.y_is_f32) {
-                float* yp = reinterpret_cast<float*>(p.y) + row * p.ldy + col0;
+          }
+          if (row_ok) {
+            if (p.y_is_f32) {
+              float* yp = reinterpret_cast<float*>(p.y) + row * p.ldy + col0;
 #pragma unroll
-                for (int g = 0; g < 4; ++g)
-                  if (col0 + g * 4 < p.N)
-                    *reinterpret_cast<float4*>(yp + g * 4) =
-                        make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
-              } else {
-                __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + row * p.ldy + col0;
+              for (int g = 0; g < 4; ++g)
+                if (col0 + g * 4 < p.N)
+                  *reinterpret_cast<float4*>(yp + g * 4) =
+                      make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+            } else {
+              __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + row * p.ldy + col0;
 #pragma unroll
-                for (int g = 0; g < 2; ++g)
-                  if (col0 + g * 8 < p.N)
-                    stg_v4(yp + g * 8,
-                           make_uint4(pack_bf16(v[8 * g], v[8 * g + 1]),
-                                      pack_bf16(v[8 * g + 2], v[8 * g + 3]),
-                                      pack_bf16(v[8 * g + 4], v[8 * g + 5]),
-                                      pack_bf16(v[8 * g + 6], v[8 * g + 7])));
-              }
+              for (int g = 0; g < 2; ++g)
+                if (col0 + g * 8 < p.N)
+                  stg_v4(yp + g * 8,
+                         make_uint4(pack_bf16(v[8 * g], v[8 * g + 1]), pack_bf16(v[8 * g + 2], v[8 * g + 3]),
+                                    pack_bf16(v[8 * g + 4], v[8 * g + 5]), pack_bf16(v[8 * g + 6], v[8 * g + 7])));
             }
-            // ---- per-column partial sums over this warp's 32 rows
-            if (want_stats) {
-              const float t1 = warp_colsum16(s1, lane);
-              const float t2 = warp_colsum16(s2, lane);
-              if ((lane & 1) == 0) {
-                stat_warp[(q * 2 + 0) * kMaxBN + j * 16 + (lane >> 1)] = t1;
-                stat_warp[(q * 2 + 1) * kMaxBN + j * 16 + (lane >> 1)] = t2;
-              }
+          }
+          if (want_stats) {
+            const float t1 = warp_colsum16(s1, lane);
+            const float t2 = warp_colsum16(s2, lane);
+            if ((lane & 1) == 0) {
+              stat_warp[(q * 2 + 0) * kMaxBN + j * 16 + (lane >> 1)] = t1;
+              stat_warp[(q * 2 + 1) * kMaxBN + j * 16 + (lane >> 1)] = t2;
             }
+          }
+        };
+
+#pragma unroll
+        for (int jj = 0; jj < 8; jj += 2) {
+          const int j = c_begin + jj;
+          if (j + 1 < c_end) {                 // 32 accumulator columns per TMEM round trip
+            float v[32];
+            tmem_ld32(t_row + j * 16, v);
+            process(v, j, rr[2 * jj], rr[2 * jj + 1]);
+            process(v + 16, j + 1, rr[2 * jj + 2], rr[2 * jj + 3]);
+          } else if (j < c_end) {
+            float v[16];
+            tmem_ld16(t_row + j * 16, v);
+            process(v, j, rr[2 * jj], rr[2 * jj + 1]);
           }
         }
         tc_fence_before();
         mbar_arrive(&tempty[buf]);
-        if (want_stats) {
-          named_bar_sync(1, 128);
-          if (et < p.block_n) {
-            const int gc = (nt - nt_begin) * p.block_n + et;
+        if (want_stats || p.epi_mode == 1) {
+          named_bar_sync(1, n_epi);
+          if (want_stats && ep_tid < p.block_n) {
+            const int gc = (nt - nt_begin) * p.block_n + ep_tid;
             float a0 = 0.f, a1 = 0.f;
 #pragma unroll
             for (int w = 0; w < 4; ++w) {
-              a0 += stat_warp[(w * 2 + 0) * kMaxBN + et];
-              a1 += stat_warp[(w * 2 + 1) * kMaxBN + et];
+              a0 += stat_warp[(w * 2 + 0) * kMaxBN + ep_tid];
+              a1 += stat_warp[(w * 2 + 1) * kMaxBN + ep_tid];
             }
             stat_acc[gc] += a0;
             stat_acc[kMaxGroupCols + gc] += a1;
           }
-          named_bar_sync(1, 128);
+          named_bar_sync(1, n_epi);
         }
       }
     if (want_stats) {
       const int gcols = (nt_end - nt_begin) * p.block_n;
-      for (int c = et; c < gcols; c += 128) {
+      for (int c = ep_tid; c < gcols; c += n_epi) {
         const int col = nt_begin * p.block_n + c;
         if (col < p.N) {
           p.stats_part[(static_cast<long long>(blockIdx.x) * 2 + 0) * p.N + col] = stat_acc[c];

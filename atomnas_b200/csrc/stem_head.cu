@@ -174,7 +174,8 @@ __device__ __forceinline__ float drop_keep_scale(unsigned long long seed, unsign
 __global__ void pool_fwd_kernel(const __nv_bfloat16* __restrict__ h, long long ldh,
                                 const float* __restrict__ scale, const float* __restrict__ shift,
                                 int act, __nv_bfloat16* pooled, long long ldp, int B, int HW, int C,
-                                float drop_p, unsigned long long seed) {
+                                float drop_p, unsigned long long seed, const unsigned long long* seed_dev) {
+  if (seed_dev != nullptr) seed += *seed_dev;
   const int ncg = C / 8;
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i >= static_cast<long long>(B) * ncg) return;
@@ -208,8 +209,10 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(
     const __nv_bfloat16* __restrict__ dpooled, long long ldd, const __nv_bfloat16* __restrict__ h,
     long long ldh, const float* __restrict__ scale, const float* __restrict__ shift,
     const float* __restrict__ mean, const float* __restrict__ rstd, int act, __nv_bfloat16* gh,
-    long long ldg, float* stats_part, int B, int HW, int C, float drop_p, unsigned long long seed) {
+    long long ldg, float* stats_part, int B, int HW, int C, float drop_p, unsigned long long seed,
+    const unsigned long long* seed_dev) {
   __shared__ float red[256 * 16];
+  if (seed_dev != nullptr) seed += *seed_dev;
   const int ncg = C / 8;
   const int lcg = threadIdx.x % 32, li = threadIdx.x / 32;
   const int cg = blockIdx.y * 32 + lcg, ch = cg * 8;
@@ -363,12 +366,12 @@ extern "C" int an_stem_wgrad(const float* x, const void* g, long long ldg, const
 
 extern "C" int an_pool_fwd(const void* h, long long ldh, const float* scale, const float* shift, int act,
                            void* pooled, long long ldp, int B, int HW, int C, float drop_p,
-                           unsigned long long seed, void* stream) {
+                           unsigned long long seed, const unsigned long long* seed_dev, void* stream) {
   AN_REQUIRE(h && pooled && C % 8 == 0 && ldh % 8 == 0 && ldp % 8 == 0, "an_pool_fwd: bad arguments");
   const long long n = static_cast<long long>(B) * (C / 8);
   pool_fwd_kernel<<<static_cast<int>((n + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(h), ldh, scale, shift, act, reinterpret_cast<__nv_bfloat16*>(pooled),
-      ldp, B, HW, C, drop_p, seed);
+      ldp, B, HW, C, drop_p, seed, seed_dev);
   AN_CHECK_LAUNCH();
   return 0;
 }
@@ -378,12 +381,13 @@ extern "C" int an_pool_bwd_stats_rows(int B) { return (B + 7) / 8; }
 extern "C" int an_pool_bwd(const void* dpooled, long long ldd, const void* h, long long ldh,
                            const float* scale, const float* shift, const float* mean, const float* rstd,
                            int act, void* gh, long long ldg, float* stats_part, int B, int HW, int C,
-                           float drop_p, unsigned long long seed, void* stream) {
+                           float drop_p, unsigned long long seed, const unsigned long long* seed_dev,
+                           void* stream) {
   AN_REQUIRE(dpooled && h && gh && stats_part && C % 8 == 0, "an_pool_bwd: bad arguments");
   dim3 grid((B + 7) / 8, (C / 8 + 31) / 32);
   pool_bwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(dpooled), ldd, reinterpret_cast<const __nv_bfloat16*>(h), ldh, scale,
-      shift, mean, rstd, act, reinterpret_cast<__nv_bfloat16*>(gh), ldg, stats_part, B, HW, C, drop_p, seed);
+      shift, mean, rstd, act, reinterpret_cast<__nv_bfloat16*>(gh), ldg, stats_part, B, HW, C, drop_p, seed, seed_dev);
   AN_CHECK_LAUNCH();
   return 0;
 }

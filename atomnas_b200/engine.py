@@ -22,6 +22,7 @@ from torch import nn
 
 from . import kernels as K
 from . import mobilenet_base as mb
+from ._lib import TAG
 
 _BF16 = torch.bfloat16
 
@@ -402,12 +403,13 @@ class Engine(object):
             K.bn_eval_coeffs(self.gamma(g)[sl], self.beta(g)[sl], self.rmean(g)[sl], self.rvar(g)[sl],
                              g.eps, C, scale, shift)
 
-    def _bn_bwd(self, g, part, rows, C=None, off=0):
+    def _bn_bwd(self, g, part, rows, C=None, off=0, raw_second=False):
         C = g.C if C is None else C
         sl = slice(off, off + C)
         K.bn_bwd_finalize(part, rows, C, g.count, self.gamma(g)[sl], self.bn_vec(g, "mean")[sl],
                           self.bn_vec(g, "rstd")[sl], self.dgamma(g)[sl], self.dbeta(g)[sl],
-                          self.bn_vec(g, "ca")[sl], self.bn_vec(g, "cb")[sl], self.bn_vec(g, "cc")[sl])
+                          self.bn_vec(g, "ca")[sl], self.bn_vec(g, "cb")[sl], self.bn_vec(g, "cc")[sl],
+                          raw_second=raw_second)
 
     def _begin_bn_step(self, training):
         """Per-forward BN bookkeeping: num_batches_tracked and the momentum to use
@@ -424,7 +426,7 @@ class Engine(object):
     # ------------------------------------------------------------------------------------------
     # forward
     # ------------------------------------------------------------------------------------------
-    def forward(self, x, training, need_grad, seed=0):
+    def forward(self, x, training, need_grad, seed=0, seed_dev=None):
         """x: fp32 NCHW (network) or NHWC bf16 [B,H,W,C] (single block).  Returns logits fp32
         [B, NC] for a network, NHWC bf16 for a block."""
         self.refresh_weights()
@@ -433,11 +435,12 @@ class Engine(object):
         else:
             B, H, W, _ = x.shape
         bf = self._buffers(B, H, W, need_grad)
-        bf.training, bf.seed = training, seed
+        bf.training, bf.seed, bf.seed_dev = training, seed, seed_dev
         self._begin_bn_step(training)
         part = bf.part
         stats = part if training else None
         if self.is_net:
+            TAG[0] = "fwd.stem"
             s = self.stem
             x = x.contiguous()
             if x.dtype != torch.float32:
@@ -456,6 +459,7 @@ class Engine(object):
             cur = self._block_fwd(p, bb, cur, B, training, stats, part)
         if not self.is_net:
             return cur.view(B, bf.blk[-1].ho, bf.blk[-1].wo, -1)
+        TAG[0] = "fwd.head"
         hd = self.head
         Mh = bf.Mh
         K.pw_gemm(cur, self.W16[hd.w16:], bf.h_raw, Mh, hd.C, hd.cin, stats_part=stats)
@@ -463,7 +467,7 @@ class Engine(object):
         drop = self.drop_p if (training and self.drop_mod.training) else 0.0
         bf.drop = drop
         K.pool_fwd(bf.h_raw, self.bn_vec(hd.bn, "scale"), self.bn_vec(hd.bn, "shift"), hd.act, bf.pooled,
-                   B, Mh // B, hd.C, ldh=hd.C, ldp=hd.C, drop_p=drop, seed=seed)
+                   B, Mh // B, hd.C, ldh=hd.C, ldp=hd.C, drop_p=drop, seed=seed, seed_dev=seed_dev)
         K.pw_gemm(bf.pooled, self.W16[hd.fw16:], bf.logits, B, hd.NCp, hd.C, bias=self.P[hd.fb_off:])
         return bf.logits[:, :hd.NC]
 
@@ -474,6 +478,7 @@ class Engine(object):
             return x
         M, Mo = bb.M, bb.Mo
         if p.expand:
+            TAG[0] = "fwd.expand"
             K.pw_gemm(x, self.W16[p.we16:], bb.e_raw, M, p.Kh, p.inp, stats_part=stats)
             self._bn_fwd(p.bn_e, part, K.pw_gemm_stats_rows(M, p.Kh), M, training)
             src, ld_src = bb.e_raw, p.Kh
@@ -481,12 +486,14 @@ class Engine(object):
         else:
             src, ld_src, e_scale, e_shift = x, p.inp, None, None
         for br in p.branches:
+            TAG[0] = "fwd.dw%d" % br.k
             K.dw_fwd(src[:, br.off:], bb.d_raw[:, br.off:], self.W32[br.wd32:], B, bb.hin, bb.win, br.hp,
                      br.k, p.stride, ldx=ld_src, ldy=p.Kh,
                      scale=None if e_scale is None else e_scale[br.off:],
                      shift=None if e_shift is None else e_shift[br.off:], act=p.act, stats_part=stats)
             self._bn_fwd(p.bn_d, part, K.dw_fwd_stats_rows(B, br.hp, bb.ho, bb.wo, br.k, p.stride), Mo,
                          training, C=br.hp, off=br.off)
+        TAG[0] = "fwd.project"
         K.pw_gemm(bb.d_raw, self.W16[p.wp16:], bb.p_raw, Mo, p.oup, p.Kh, a_mode=1, a_act=p.act,
                   a1=self.bn_vec(p.bn_d, "scale"), a3=self.bn_vec(p.bn_d, "shift"), stats_part=stats)
         self._bn_fwd(p.bn_p, part, K.pw_gemm_stats_rows(Mo, p.oup), Mo, training)
@@ -507,6 +514,7 @@ class Engine(object):
         part, wpart = bf.part, bf.wpart
         G, P = self.G, self.P
         if self.is_net:
+            TAG[0] = "bwd.head"
             hd = self.head
             Mh = bf.Mh
             dl = bf.dlogits
@@ -519,7 +527,7 @@ class Engine(object):
             K.pw_gemm(dl, self.W16[hd.fwT16:], bf.dpool, B, hd.C, hd.NCp)
             K.pool_bwd(bf.dpool, bf.h_raw, self.bn_vec(hd.bn, "scale"), self.bn_vec(hd.bn, "shift"),
                        self.bn_vec(hd.bn, "mean"), self.bn_vec(hd.bn, "rstd"), hd.act, bf.gh, part, B,
-                       Mh // B, hd.C, ldd=hd.C, ldh=hd.C, ldg=hd.C, drop_p=bf.drop, seed=bf.seed)
+                       Mh // B, hd.C, ldd=hd.C, ldh=hd.C, ldg=hd.C, drop_p=bf.drop, seed=bf.seed, seed_dev=bf.seed_dev)
             self._bn_bwd(hd.bn, part, K.pool_bwd_stats_rows(B))
             ca, cb, cc = (self.bn_vec(hd.bn, n) for n in ("ca", "cb", "cc"))
             y_last = bf.blk[-1].y if self.blocks else bf.y0
@@ -544,6 +552,7 @@ class Engine(object):
         if not self.is_net:
             b0 = bf.blk[0]
             return dy[:b0.M * self.blocks[0].inp].view(B, b0.hin, b0.win, -1)
+        TAG[0] = "bwd.stem"
         s = self.stem
         h, w = bf.s_hw
         M0 = B * h * w
@@ -568,6 +577,7 @@ class Engine(object):
         M, Mo = bb.M, bb.Mo
         act = p.act
         # pw_bn backward: reductions over (dy, p_raw), then dp_raw = ca*dy + cb*p_raw + cc
+        TAG[0] = "bwd.pw_bn"
         K.col_reduce(dy, part, Mo, p.oup, ldg=p.oup, x=bb.p_raw, ldx=p.oup,
                      mean=self.bn_vec(p.bn_p, "mean"), rstd=self.bn_vec(p.bn_p, "rstd"))
         self._bn_bwd(p.bn_p, part, K.col_reduce_rows(Mo, p.oup))
@@ -576,15 +586,17 @@ class Engine(object):
                      a1=self.bn_vec(p.bn_p, "ca"), a2=self.bn_vec(p.bn_p, "cb"), a3=self.bn_vec(p.bn_p, "cc"))
         d_scale, d_shift = self.bn_vec(p.bn_d, "scale"), self.bn_vec(p.bn_d, "shift")
         # project weight gradient: dWp[oup, h_i] = dp^T act(bn(d_raw))
+        TAG[0] = "bwd.project_wgrad"
         sp = K.pw_wgrad(bb.d_raw, dp, wpart, Mo, p.Kh, p.oup, p_mode=1, p_act=act, a1=d_scale, a3=d_shift)
         for br in p.branches:
             K.wgrad_reduce(wpart, sp, p.Kh, p.oup, G[br.wp_off:], 1, br.h, row0=br.off, nrows=br.h)
         # project data gradient with act/BN backward epilogue -> g_d
         g_d = bf.g_d
+        TAG[0] = "bwd.project_dgrad"
         K.pw_gemm(dp, self.W16[p.wpT16:], g_d, Mo, p.Kh, p.oup, epi_mode=1, r=bb.d_raw, ldr=p.Kh,
                   r_scale=d_scale, r_shift=d_shift, r_mean=self.bn_vec(p.bn_d, "mean"),
                   r_rstd=self.bn_vec(p.bn_d, "rstd"), r_act=act, stats_part=part)
-        self._bn_bwd(p.bn_d, part, K.pw_gemm_stats_rows(Mo, p.Kh))
+        self._bn_bwd(p.bn_d, part, K.pw_gemm_stats_rows(Mo, p.Kh), raw_second=True)
         dca, dcb, dcc = (self.bn_vec(p.bn_d, n) for n in ("ca", "cb", "cc"))
         if p.expand:
             src, ld_src = bb.e_raw, p.Kh
@@ -600,6 +612,7 @@ class Engine(object):
 
         for br in p.branches:
             o = br.off
+            TAG[0] = "bwd.dw%d_wgrad" % br.k
             if br.hp == br.h:
                 K.dw_bwd_weight(g_d[o:], bb.d_raw[:, o:], src[:, o:], dca[o:], dcb[o:], dcc[o:],
                                 sl(e_scale, br), sl(e_shift, br), act if p.expand else 0, wpart,
@@ -607,6 +620,7 @@ class Engine(object):
                                 lde=ld_src)
             else:
                 self._dw_wgrad_padded(p, bb, br, g_d, src, ld_src, dca, dcb, dcc, e_scale, e_shift, B, wpart)
+            TAG[0] = "bwd.dw%d_dgrad" % br.k
             K.dw_bwd_data(g_d[o:], bb.d_raw[:, o:], src[:, o:], ge[o:], self.W32[br.wd32:], dca[o:], dcb[o:],
                           dcc[o:], sl(e_scale, br), sl(e_shift, br), sl(e_mean, br), sl(e_rstd, br),
                           part if p.expand else None, act if p.expand else 0, B, bb.hin, bb.win, br.hp, br.k,
@@ -619,9 +633,11 @@ class Engine(object):
                 K.affine_act(ge, dx, M, p.inp, ld1=p.inp, ldo=p.inp, x2=dy, ld2=p.oup)
             return
         eca, ecb, ecc = (self.bn_vec(p.bn_e, n) for n in ("ca", "cb", "cc"))
+        TAG[0] = "bwd.expand_wgrad"
         sp = K.pw_wgrad(ge, bb.x, wpart, M, p.Kh, p.inp, p2=bb.e_raw, p_mode=2, a1=eca, a2=ecb, a3=ecc)
         for br in p.branches:
             K.wgrad_reduce(wpart, sp, p.Kh, p.inp, G[br.we_off:], p.inp, 1, row0=br.off, nrows=br.h)
+        TAG[0] = "bwd.expand_dgrad"
         K.pw_gemm(ge, self.W16[p.weT16:], dx, M, p.inp, p.Kh, x2=bb.e_raw, a_mode=2, a1=eca, a2=ecb, a3=ecc,
                   epi_mode=2, r=dy if p.res else None, ldr=p.oup)
 

@@ -131,10 +131,10 @@ def bn_finalize(part, rows, C, count, gamma, beta, rm, rv, momentum, eps, mean, 
                                    L.stream_ptr()), "an_bn_finalize")
 
 
-def bn_bwd_finalize(part, rows, C, count, gamma, mean, rstd, dgamma, dbeta, ca, cb, cc):
+def bn_bwd_finalize(part, rows, C, count, gamma, mean, rstd, dgamma, dbeta, ca, cb, cc, raw_second=False):
     L.check(L.lib().an_bn_bwd_finalize(_c(part), rows, C, float(count), _c(gamma), _c(mean),
                                        _c(rstd), _c(dgamma), _c(dbeta), _c(ca), _c(cb), _c(cc),
-                                       L.stream_ptr()), "an_bn_bwd_finalize")
+                                       1 if raw_second else 0, L.stream_ptr()), "an_bn_bwd_finalize")
 
 
 def affine_act(x1, out, M, C, *, ld1, ldo, x2=None, ld2=0, a1=None, a2=None, a3=None, act=0):
@@ -172,9 +172,9 @@ def stem_wgrad(x, g, sraw, ca, cb, cc, partials, dw, B, H, W, C, *, ldg, lds):
                                   _c(partials), _c(dw), B, H, W, C, L.stream_ptr()), "an_stem_wgrad")
 
 
-def pool_fwd(h, scale, shift, act, pooled, B, HW, C, *, ldh, ldp, drop_p=0.0, seed=0):
+def pool_fwd(h, scale, shift, act, pooled, B, HW, C, *, ldh, ldp, drop_p=0.0, seed=0, seed_dev=None):
     L.check(L.lib().an_pool_fwd(_c(h), ldh, _c(scale), _c(shift), act, _c(pooled), ldp, B, HW, C,
-                                drop_p, seed, L.stream_ptr()), "an_pool_fwd")
+                                drop_p, seed, _c(seed_dev), L.stream_ptr()), "an_pool_fwd")
 
 
 def pool_bwd_stats_rows(B):
@@ -182,10 +182,10 @@ def pool_bwd_stats_rows(B):
 
 
 def pool_bwd(dpooled, h, scale, shift, mean, rstd, act, gh, part, B, HW, C, *, ldd, ldh, ldg,
-             drop_p=0.0, seed=0):
+             drop_p=0.0, seed=0, seed_dev=None):
     L.check(L.lib().an_pool_bwd(_c(dpooled), ldd, _c(h), ldh, _c(scale), _c(shift), _c(mean),
                                 _c(rstd), act, _c(gh), ldg, _c(part), B, HW, C, drop_p, seed,
-                                L.stream_ptr()), "an_pool_bwd")
+                                _c(seed_dev), L.stream_ptr()), "an_pool_bwd")
 
 
 def ce_loss(logits, labels, B, NC, eps, grad_scale, loss, dlogits, *, ldl, ldd, nd_pad):
@@ -202,15 +202,16 @@ def f32_to_bf16(src, dst, rows, cols, cols_pad, *, lds, ldd):
 # optimizer / weights
 # ------------------------------------------------------------------------------------------------
 def rmsprop_ema_step(p, g, sq, buf, ema, wd_flag, l1_pen, n, lr, alpha, momentum, eps,
-                     eps_inside_sqrt, grad_scale, weight_decay, rho, ema_decay):
+                     eps_inside_sqrt, grad_scale, weight_decay, rho, ema_decay, hparams_dev=None):
     L.check(L.lib().an_rmsprop_ema_step(_c(p), _c(g), _c(sq), _c(buf), _c(ema), _c(wd_flag),
                                         _c(l1_pen), n, lr, alpha, momentum, eps,
                                         1 if eps_inside_sqrt else 0, grad_scale, weight_decay, rho,
-                                        ema_decay, L.stream_ptr()), "an_rmsprop_ema_step")
+                                        ema_decay, _c(hparams_dev), L.stream_ptr()), "an_rmsprop_ema_step")
 
 
-def ema_update(ema, x, n, decay):
-    L.check(L.lib().an_ema_update(_c(ema), _c(x), n, decay, L.stream_ptr()), "an_ema_update")
+def ema_update(ema, x, n, decay, hparams_dev=None):
+    L.check(L.lib().an_ema_update(_c(ema), _c(x), n, decay, _c(hparams_dev), L.stream_ptr()),
+            "an_ema_update")
 
 
 def reg_losses(p, wd_flag, l1_pen, n, part):

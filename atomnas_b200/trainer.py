@@ -39,6 +39,9 @@ class Trainer(object):
         if prune_penalties:
             eng.set_l1_penalties(prune_penalties, dict(model.named_parameters()))
         self.num_updates = 0
+        self.hp_dev = torch.zeros(4, device=eng.dev)                       # lr, rho, ema decay
+        self.seed_dev = torch.zeros(1, device=eng.dev, dtype=torch.int64)  # dropout stream position
+        self.launches_per_step = None
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.bucket_elems = max(1, bucket_bytes // 4)
         self._handles = []
@@ -67,56 +70,60 @@ class Trainer(object):
         self._pending_hi = None
 
     # ---- one step on device tensors ---------------------------------------------------------------
-    def _step_impl(self, x, target, rho, lr):
-        eng = self.eng
+    def _push_hparams(self, rho, lr):
+        """Per-step scalars live in device memory ({lr, rho, ema_decay}) so the same launch
+        sequence -- or a captured CUDA graph of it -- serves every step of the schedules."""
         self.num_updates += 1
-        eng.forward(x, True, True, seed=self.num_updates)
+        d = 0.0
+        if self.ema_decay:
+            d = min(self.ema_decay, (1.0 + self.num_updates) / (10.0 + self.num_updates))
+        self.hp_dev.copy_(torch.tensor([lr, rho, d, 0.0]))
+
+    def _step_impl(self, x, target):
+        eng = self.eng
+        self.seed_dev.add_(1)                      # dropout stream advances on the device
+        eng.forward(x, True, True, seed=0x5EED, seed_dev=self.seed_dev)
         loss = eng.loss_and_dlogits(target, self.label_smoothing, 1.0)
         eng.backward(None, grad_ready=self._grad_ready)
         self._finish_allreduce()
-        d = 0.0
-        ema = None
+        K.rmsprop_ema_step(eng.P, eng.G, self.sq, self.buf, self.ema_P, eng.wd_flag, eng.l1_pen, eng.n_params,
+                           0.0, self.alpha, self.momentum, self.eps, self.eps_inside_sqrt, 1.0 / self.world,
+                           self.weight_decay, 0.0, 0.0, hparams_dev=self.hp_dev)
         if self.ema_decay:
-            d = min(self.ema_decay, (1.0 + self.num_updates) / (10.0 + self.num_updates))
-            ema = self.ema_P
-        K.rmsprop_ema_step(eng.P, eng.G, self.sq, self.buf, ema, eng.wd_flag, eng.l1_pen, eng.n_params, lr,
-                           self.alpha, self.momentum, self.eps, self.eps_inside_sqrt, 1.0 / self.world,
-                           self.weight_decay, rho, d)
-        if self.ema_decay:
-            K.ema_update(self.ema_S, eng.S, eng.S.numel(), d)
+            K.ema_update(self.ema_S, eng.S, eng.S.numel(), 0.0, hparams_dev=self.hp_dev)
         eng.refresh_weights(force=True)
         return loss
 
     def step(self, x, target, rho=0.0, lr=None):
         """x: fp32 NCHW on the device, target: int64 labels.  Returns per-sample losses (device)."""
         lr = self.lr if lr is None else lr
+        self._push_hparams(rho, lr)
         if not self.use_cuda_graph:
-            return self._step_impl(x, target, rho, lr)
-        return self._step_graphed(x, target, rho, lr)
+            return self._step_impl(x, target)
+        return self._step_graphed(x, target)
 
-    def _step_graphed(self, x, target, rho, lr):
-        """Whole step replayed from a CUDA graph (launch-bound inner loop; hyper-parameters are
-        baked at capture time, so the graph is re-captured when lr / rho change)."""
-        key = (tuple(x.shape), float(rho), float(lr))
+    def _step_graphed(self, x, target):
+        """Whole step replayed from a CUDA graph (the ~900 launches of a step are launch-bound
+        from Python); lr / rho / EMA decay / dropout seed are read from device memory."""
+        key = tuple(x.shape)
         if self._graph is None or self._static[2] != key:
             sx, sy = x.clone(), target.clone()
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                for _ in range(2):                         # warm-up outside capture
-                    self._step_impl(sx, sy, rho, lr)
+                first = self._step_impl(sx, sy).clone()    # this step runs eagerly (also the warm-up)
             torch.cuda.current_stream().wait_stream(side)
             self._graph = torch.cuda.CUDAGraph()
-            n0 = self.num_updates
-            with torch.cuda.graph(self._graph):
-                out = self._step_impl(sx, sy, rho, lr)
-            self.num_updates = n0 + 1
+            from ._lib import lib
+            c0 = lib().an_launch_count()
+            with torch.cuda.graph(self._graph):            # capture records, it does not execute
+                out = self._step_impl(sx, sy)
+            self.launches_per_step = lib().an_launch_count() - c0     # kernel nodes replayed per step
             self._static = (sx, sy, key, out)
-            return out
+            return first
         sx, sy, _, out = self._static
         sx.copy_(x, non_blocking=True)
         sy.copy_(target, non_blocking=True)
-        self.num_updates += 1
         self._graph.replay()
         return out
 

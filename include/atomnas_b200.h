@@ -31,6 +31,8 @@ const char* an_last_error(void);
 int an_version(void);
 /* number of SMs of the current device (grid sizing of the persistent kernels) */
 int an_sm_count(void);
+/* kernels launched by this library so far in this process (bench.py "gpu_launches") */
+long long an_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------
  * Pointwise (1x1) convolution as a tcgen05 GEMM:   D[M,N] = Aeff[M,K] * W[N,K]^T
@@ -45,8 +47,9 @@ int an_sm_count(void);
  * Epilogue:
  *   epi_mode 0: y = D (+ bias[n]); optional per-column sum / sum-of-squares partials of the
  *               ROUNDED output (training-mode BN statistics, F.batch_norm)
- *   epi_mode 1: g = D * act'(r_scale*r + r_shift); y = g; partials of sum(g), sum(g*xhat),
- *               xhat = (r - r_mean)*r_rstd            (ReLU backward + BN-backward reductions)
+ *   epi_mode 1: g = D * act'(r_scale*r + r_shift); y = g; partials of sum(g), sum(g*r)
+ *               (activation backward + BN-backward reductions; an_bn_bwd_finalize(raw_second=1)
+ *               centres the second moment)
  *   epi_mode 2: y = D + r                             (residual gradient add; r may be NULL)
  * stats_part, when not NULL, receives an_pw_gemm_stats_rows(M,N) rows of [2][N] floats.
  * ------------------------------------------------------------------------------------------ */
@@ -141,6 +144,7 @@ int an_dw_bwd_weight_rows(int B, int C, int H, int W, int k, int stride);
  *   an_bn_finalize     : mean/rstd (saved for backward), scale = gamma*rstd, shift = beta-mean*scale,
  *                        running stats update (momentum m; calibration passes m = 1/nbt)
  *   an_bn_bwd_finalize : dgamma = sum g*xhat, dbeta = sum g, and (ca,cb,cc) with dx = ca*g+cb*x+cc
+ *                        (raw_second: the partials hold sum g*x -- an_pw_gemm epi_mode 1)
  *   an_affine_act      : out = act(a1*x1 + a2*x2 + a3) (NULL coefficient = 1, 1, 0; x2 optional):
  *                        pw_bn apply + residual (:379-381), BN-backward apply
  *   an_col_reduce      : partials of sum g, sum g*xhat over a [M,C] matrix (pw_bn backward)
@@ -150,7 +154,7 @@ int an_bn_finalize(const float* stats_part, int rows, int C, double count, const
                    float eps, float* mean, float* rstd, float* scale, float* shift, void* stream);
 int an_bn_bwd_finalize(const float* stats_part, int rows, int C, double count, const float* gamma,
                        const float* mean, const float* rstd, float* dgamma, float* dbeta, float* ca,
-                       float* cb, float* cc, void* stream);
+                       float* cb, float* cc, int raw_second, void* stream);
 int an_affine_act(const void* x1, long long ld1, const void* x2, long long ld2, const float* a1,
                   const float* a2, const float* a3, int act, void* out, long long ldo, long long M,
                   int C, void* stream);
@@ -181,11 +185,11 @@ int an_stem_wgrad(const float* x, const void* g, long long ldg, const void* sraw
 int an_stem_wgrad_rows(int B, int Ho, int Wo);
 int an_pool_fwd(const void* h, long long ldh, const float* scale, const float* shift, int act,
                 void* pooled, long long ldp, int B, int HW, int C, float drop_p,
-                unsigned long long seed, void* stream);
+                unsigned long long seed, const unsigned long long* seed_dev, void* stream);
 int an_pool_bwd(const void* dpooled, long long ldd, const void* h, long long ldh, const float* scale,
                 const float* shift, const float* mean, const float* rstd, int act, void* gh,
                 long long ldg, float* stats_part, int B, int HW, int C, float drop_p,
-                unsigned long long seed, void* stream);
+                unsigned long long seed, const unsigned long long* seed_dev, void* stream);
 int an_pool_bwd_stats_rows(int B);
 int an_ce_loss(const float* logits, long long ldl, const long long* labels, int B, int NC,
                float label_smoothing, float grad_scale, float* loss, void* dlogits, long long ldd,
@@ -198,6 +202,9 @@ int an_f32_to_bf16(const float* src, long long lds, void* dst, long long ldd, lo
  * wd_flag < 0 marks frozen padding elements):
  *   g' = g*grad_scale + weight_decay*wd_flag*p + rho*l1_pen*sign(p)
  *   RMSprop (utils/rmsprop.py:100-130), then ema = d*ema + (1-d)*p (utils/optim.py:64-65).
+ * hparams_dev (optional, device) = {lr, rho, ema_decay}: per-step values read on the device so a
+ * captured CUDA graph can be replayed while the schedules advance; seed_dev likewise offsets the
+ * dropout seed (effective seed = seed + *seed_dev).
  * an_refresh_weights re-materialises the kernel-layout weight copies (bf16 [N,K], bf16 [K,N]
  * transposes for dgrad, fp32 tap-major depthwise) from the fp32 master arena via a table of
  * 9 x int64 entries {src_ld, src_off, dst_off, rows, cols, dst_ld, transpose, dst_f32, first_tile}.
@@ -207,8 +214,9 @@ int an_rmsprop_ema_step(float* p, const float* g, float* sq, float* buf, float* 
                         const float* wd_flag, const float* l1_pen, long long n, float lr,
                         float alpha, float momentum, float eps, int eps_inside_sqrt,
                         float grad_scale, float weight_decay, float rho, float ema_decay,
-                        void* stream);
-int an_ema_update(float* ema, const float* x, long long n, float decay, void* stream);
+                        const float* hparams_dev, void* stream);
+int an_ema_update(float* ema, const float* x, long long n, float decay, const float* hparams_dev,
+                  void* stream);
 int an_reg_losses(const float* p, const float* wd_flag, const float* l1_pen, long long n,
                   float* part, void* stream);
 int an_refresh_weights(const void* table, int n_entries, long long total_tiles, const float* src,
