@@ -54,7 +54,8 @@ __global__ void dw_fwd_kernel(const DwFwdParams p) {
   // weights -> smem (zero for channels beyond C)
   for (int i = tid; i < K * K * ncg * 8; i += nthreads) {
     const int tap = i / (ncg * 8), c = cb0 + i % (ncg * 8);
-    wsm[i] = (c < p.C) ? p.w[(long long)tap * p.C + c] : 0.f;
+    const int e8 = i % 8, lcg8 = (i % (ncg * 8)) / 8;      // [tap][half][cg][4]: 16-byte lane stride
+    wsm[((tap * 2 + e8 / 4) * ncg + lcg8) * 4 + (e8 & 3)] = (c < p.C) ? p.w[(long long)tap * p.C + c] : 0.f;
   }
   float sc[8], sh[8];
 #pragma unroll
@@ -112,8 +113,8 @@ __global__ void dw_fwd_kernel(const DwFwdParams p) {
         float wr[K][8];
 #pragma unroll
         for (int kc = 0; kc < K; ++kc) {
-          const float4 lo = *reinterpret_cast<const float4*>(wsm + ((kr * K + kc) * ncg + cg) * 8);
-          const float4 hi = *reinterpret_cast<const float4*>(wsm + ((kr * K + kc) * ncg + cg) * 8 + 4);
+          const float4 lo = *reinterpret_cast<const float4*>(wsm + (((kr * K + kc) * 2 + 0) * ncg + cg) * 4);
+          const float4 hi = *reinterpret_cast<const float4*>(wsm + (((kr * K + kc) * 2 + 1) * ncg + cg) * 4);
           wr[kc][0] = lo.x; wr[kc][1] = lo.y; wr[kc][2] = lo.z; wr[kc][3] = lo.w;
           wr[kc][4] = hi.x; wr[kc][5] = hi.y; wr[kc][6] = hi.z; wr[kc][7] = hi.w;
         }
@@ -182,13 +183,34 @@ struct DwCfg {
   size_t smem;
 };
 
+// Channel groups (8 channels each) per CTA: the largest count <= 16 that tiles C/8 without a
+// half-empty last block (branch widths are 6*Cin: 96, 144, 240, ... -- multiples of 48, not 64).
+static int pick_ncg(int C) {
+  const int g = (C + 7) / 8;
+  if (g <= 16) return g;
+  int best = 8;
+  double best_util = 0.0;
+  for (int n = 16; n >= 6; --n) {
+    const int blocks = (g + n - 1) / n;
+    const double util = static_cast<double>(g) / (blocks * n);
+    if (util > best_util + 1e-9) { best_util = util; best = n; }
+  }
+  return best;
+}
+
+static void pick_tile(DwCfg* c, int C, int out_h, int out_w, bool wide_ok) {
+  c->ncg = pick_ncg(C);
+  c->tc = (out_w > 8 && wide_ok) ? 2 : 1;
+  if (c->ncg <= 4) c->tc = (out_w > 16) ? 4 : c->tc;
+  c->tr = 128 / (c->ncg * c->tc);
+  if (c->tr < 4) c->tr = 4;
+  if (c->tr > 16) c->tr = 16;
+  if (c->tr > out_h) c->tr = out_h;
+}
+
 static DwCfg dw_fwd_cfg(int B, int C, int Ho, int Wo, int k, int s) {
   DwCfg c;
-  if (C >= 128 && Wo <= 8) { c.ncg = 16; c.tc = 1; c.tr = 8; }
-  else if (C >= 64) { c.ncg = 8; c.tc = (Wo > 8 && s == 1) ? 2 : 1; c.tr = 8; }
-  else if (C >= 32) { c.ncg = 4; c.tc = 2; c.tr = 16; }
-  else { c.ncg = (C + 7) / 8; c.tc = 4; c.tr = 16; }
-  if (c.tr > Ho) c.tr = Ho;
+  pick_tile(&c, C, Ho, Wo, s == 1);
   c.threads = c.ncg * c.tr * c.tc;
   c.tiles_x = (Wo + c.tc * 8 - 1) / (c.tc * 8);
   c.tiles_y = (Ho + c.tr - 1) / c.tr;
@@ -296,7 +318,8 @@ __global__ void dw_bwd_data_kernel(const DwBwdDataParams p) {
 
   for (int i = tid; i < K * K * ncg * 8; i += nthreads) {
     const int tap = i / (ncg * 8), c = cb0 + i % (ncg * 8);
-    wsm[i] = (c < p.C) ? p.w[(long long)tap * p.C + c] : 0.f;
+    const int e8 = i % 8, lcg8 = (i % (ncg * 8)) / 8;      // [tap][half][cg][4]: 16-byte lane stride
+    wsm[((tap * 2 + e8 / 4) * ncg + lcg8) * 4 + (e8 & 3)] = (c < p.C) ? p.w[(long long)tap * p.C + c] : 0.f;
   }
   float st1[8], st2[8];
 #pragma unroll
@@ -349,8 +372,8 @@ __global__ void dw_bwd_data_kernel(const DwBwdDataParams p) {
         float wr[K][8];
 #pragma unroll
         for (int kc = 0; kc < K; ++kc) {
-          const float4 lo = *reinterpret_cast<const float4*>(wsm + ((kr * K + kc) * ncg + cg) * 8);
-          const float4 hi = *reinterpret_cast<const float4*>(wsm + ((kr * K + kc) * ncg + cg) * 8 + 4);
+          const float4 lo = *reinterpret_cast<const float4*>(wsm + (((kr * K + kc) * 2 + 0) * ncg + cg) * 4);
+          const float4 hi = *reinterpret_cast<const float4*>(wsm + (((kr * K + kc) * 2 + 1) * ncg + cg) * 4);
           wr[kc][0] = lo.x; wr[kc][1] = lo.y; wr[kc][2] = lo.z; wr[kc][3] = lo.w;
           wr[kc][4] = hi.x; wr[kc][5] = hi.y; wr[kc][6] = hi.z; wr[kc][7] = hi.w;
         }
@@ -424,11 +447,7 @@ __global__ void dw_bwd_data_kernel(const DwBwdDataParams p) {
 
 static DwCfg dw_bwd_data_cfg(int B, int C, int H, int W, int k, int s) {
   DwCfg c;
-  if (C >= 128 && W <= 8) { c.ncg = 16; c.tc = 1; c.tr = 8; }
-  else if (C >= 64) { c.ncg = 8; c.tc = (W > 8) ? 2 : 1; c.tr = 8; }
-  else if (C >= 32) { c.ncg = 4; c.tc = 2; c.tr = 16; }
-  else { c.ncg = (C + 7) / 8; c.tc = 4; c.tr = 16; }
-  if (c.tr > H) c.tr = H;
+  pick_tile(&c, C, H, W, true);
   c.threads = c.ncg * c.tr * c.tc;
   c.tiles_x = (W + c.tc * 8 - 1) / (c.tc * 8);
   c.tiles_y = (H + c.tr - 1) / c.tr;
@@ -596,7 +615,8 @@ struct DwWgCfg {
 
 static DwWgCfg dw_bwd_weight_cfg(int B, int C, int Ho, int Wo, int k, int s) {
   DwWgCfg c;
-  c.ncg = C >= 64 ? 8 : (C + 7) / 8;
+  c.ncg = pick_ncg(C);
+  if (c.ncg > 12) c.ncg = (c.ncg + 1) / 2;
   c.two = (Wo > 8 && s == 1) ? 16 : 8;
   c.tro = Ho < 8 ? Ho : 8;
   c.rl = 256 / (c.ncg * k);

@@ -696,6 +696,18 @@ def _act_of(module):
 # module -> engine registry, autograd glue
 # ------------------------------------------------------------------------------------------------
 _ENGINES = weakref.WeakKeyDictionary()
+_PARAM_OWNER = {}          # id(param) -> (weakref(param), weakref(engine))
+
+
+def engine_of_param(p):
+    """The live engine whose arena currently backs parameter `p` (None if there is none)."""
+    rec = _PARAM_OWNER.get(id(p))
+    if rec is None or rec[0]() is not p:
+        return None
+    eng = rec[1]()
+    if eng is None or eng.root_ref() is None or _ENGINES.get(eng.root_ref()) is not eng:
+        return None
+    return eng
 
 
 def get_engine(root):
@@ -705,7 +717,15 @@ def get_engine(root):
     if eng is None:
         eng = Engine(root)
         _ENGINES[root] = eng
+        for p in eng.params():
+            _PARAM_OWNER[id(p)] = (weakref.ref(p), weakref.ref(eng))
+        for mod, attr, _, _ in eng.buf_slots:
+            t = getattr(mod, attr)
+            _PARAM_OWNER[id(t)] = (weakref.ref(t), weakref.ref(eng))
     return eng
+
+
+engine_of_tensor = engine_of_param
 
 
 def _still_valid(eng, root):
