@@ -75,11 +75,11 @@ SIGNATURES = {
                                   c_ll, c_int, c_fp, c_vp]),
     "an_sum_rows": (c_int, [c_fp, c_int, c_ll, c_ll, c_fp, c_vp]),
     "an_dw_fwd": (c_int, [ctypes.POINTER(DwFwdArgs), c_vp]),
-    "an_dw_fwd_stats_rows": (c_int, [c_int] * 6),
+    "an_dw_fwd_stats_rows": (c_int, [c_int] * 7),
     "an_dw_bwd_data": (c_int, [ctypes.POINTER(DwBwdArgs), c_vp]),
-    "an_dw_bwd_data_stats_rows": (c_int, [c_int] * 6),
+    "an_dw_bwd_data_stats_rows": (c_int, [c_int] * 7),
     "an_dw_bwd_weight": (c_int, [ctypes.POINTER(DwBwdArgs), c_fp, c_fp, c_vp]),
-    "an_dw_bwd_weight_rows": (c_int, [c_int] * 6),
+    "an_dw_bwd_weight_rows": (c_int, [c_int] * 7),
     "an_bn_finalize": (c_int, [c_fp, c_int, c_int, c_d, c_fp, c_fp, c_fp, c_fp, c_f, c_f, c_fp,
                                c_fp, c_fp, c_fp, c_vp]),
     "an_bn_bwd_finalize": (c_int, [c_fp, c_int, c_int, c_d, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp,

@@ -54,6 +54,11 @@ int sm_count();
 int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer,
                       uint64_t ld_elems, uint32_t box_inner, uint32_t box_outer);
 
+// 4-D bf16 NHWC tensor [B, H, W, C] (row pitch ld_elems per pixel), un-swizzled boxes
+// {box_c, box_w, box_h, 1}; coordinates may be negative / out of range (zero fill = conv padding).
+int make_tmap_bf16_nhwc(CUtensorMap* tm, const void* base, uint64_t C, uint64_t W, uint64_t H,
+                        uint64_t B, uint64_t ld_elems, uint32_t box_c, uint32_t box_w, uint32_t box_h);
+
 #ifdef __CUDACC__
 // ----------------------------------------------------------------------------------------------
 // small device helpers
@@ -163,6 +168,16 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
       " [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)),
         "r"(c_inner), "r"(c_outer)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar,
+                                            int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)),
+        "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 

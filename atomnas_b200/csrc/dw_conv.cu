@@ -239,7 +239,16 @@ static int launch_dw_fwd(const DwFwdParams& p, const DwCfg& c, cudaStream_t st) 
 
 using namespace an;
 
-extern "C" int an_dw_fwd_stats_rows(int B, int C, int Ho, int Wo, int k, int stride) {
+namespace an {   // stride-1 row-streaming kernels (dw_conv_s1.cu)
+int dw_s1_fwd_rows(int B, int C, int H, int W, int k);
+int dw_s1_wgrad_rows(int B, int C, int H, int W, int k);
+int dw_s1_fwd(const an_dw_fwd_args* a, cudaStream_t st);
+int dw_s1_bwd_data(const an_dw_bwd_args* a, cudaStream_t st);
+int dw_s1_wgrad(const an_dw_bwd_args* a, float* partials, cudaStream_t st);
+}
+
+extern "C" int an_dw_fwd_stats_rows(int B, int C, int Ho, int Wo, int k, int stride, int fused) {
+  if (stride == 1 && !fused) return dw_s1_fwd_rows(B, C, Ho, Wo, k);
   return dw_fwd_cfg(B, C, Ho, Wo, k, stride).parts;
 }
 
@@ -247,6 +256,7 @@ extern "C" int an_dw_fwd(const an_dw_fwd_args* a, void* stream) {
   AN_REQUIRE(a->k == 3 || a->k == 5 || a->k == 7, "an_dw_fwd: kernel size %d unsupported", a->k);
   AN_REQUIRE(a->stride == 1 || a->stride == 2, "an_dw_fwd: stride %d unsupported", a->stride);
   AN_REQUIRE(a->C % 8 == 0 && a->ldx % 8 == 0 && a->ldy % 8 == 0, "an_dw_fwd: channels/pitches must be multiples of 8");
+  if (a->stride == 1 && a->scale == nullptr) return dw_s1_fwd(a, static_cast<cudaStream_t>(stream));
   const int P = (a->k - 1) / 2;
   const int Ho = (a->H + 2 * P - a->k) / a->stride + 1, Wo = (a->W + 2 * P - a->k) / a->stride + 1;
   const DwCfg c = dw_fwd_cfg(a->B, a->C, Ho, Wo, a->k, a->stride);
@@ -337,20 +347,24 @@ __global__ void dw_bwd_data_kernel(const DwBwdDataParams p) {
       if (ho >= 0 && ho < p.Ho && wo >= 0 && wo < p.Wo && ch < p.C) {
         const long long pix = ((long long)n * p.Ho + ho) * p.Wo + wo;
         const uint4 gv = ldg_nc_v4(p.g + pix * p.ldg + ch);
-        const uint4 dv = ldg_nc_v4(p.draw + pix * p.ldd + ch);
-        float a[8], b[8], c[8];
-        load_coef8(p.ca, ch, p.C, a, 0.f);
-        load_coef8(p.cb, ch, p.C, b, 0.f);
-        load_coef8(p.cc, ch, p.C, c, 0.f);
-        const uint32_t gi[4] = {gv.x, gv.y, gv.z, gv.w}, di[4] = {dv.x, dv.y, dv.z, dv.w};
-        uint32_t o[4];
+        if (p.ca == nullptr) {
+          v = gv;                                   // dd already materialised
+        } else {
+          const uint4 dv = ldg_nc_v4(p.draw + pix * p.ldd + ch);
+          float a[8], b[8], c[8];
+          load_coef8(p.ca, ch, p.C, a, 0.f);
+          load_coef8(p.cb, ch, p.C, b, 0.f);
+          load_coef8(p.cc, ch, p.C, c, 0.f);
+          const uint32_t gi[4] = {gv.x, gv.y, gv.z, gv.w}, di[4] = {dv.x, dv.y, dv.z, dv.w};
+          uint32_t o[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float lo = fmaf(a[2 * e], bf16_lo(gi[e]), fmaf(b[2 * e], bf16_lo(di[e]), c[2 * e]));
-          const float hi = fmaf(a[2 * e + 1], bf16_hi(gi[e]), fmaf(b[2 * e + 1], bf16_hi(di[e]), c[2 * e + 1]));
-          o[e] = pack_bf16(lo, hi);
+          for (int e = 0; e < 4; ++e) {
+            const float lo = fmaf(a[2 * e], bf16_lo(gi[e]), fmaf(b[2 * e], bf16_lo(di[e]), c[2 * e]));
+            const float hi = fmaf(a[2 * e + 1], bf16_hi(gi[e]), fmaf(b[2 * e + 1], bf16_hi(di[e]), c[2 * e + 1]));
+            o[e] = pack_bf16(lo, hi);
+          }
+          v = make_uint4(o[0], o[1], o[2], o[3]);
         }
-        v = make_uint4(o[0], o[1], o[2], o[3]);
       }
       patch[i] = v;
     }
@@ -543,18 +557,22 @@ __global__ void dw_bwd_weight_kernel(const DwBwdWeightParams p) {
         if (oy < p.Ho && ox < p.Wo && ch < p.C) {
           const long long pix = ((long long)n * p.Ho + oy) * p.Wo + ox;
           const uint4 gv = ldg_nc_v4(p.g + pix * p.ldg + ch);
-          const uint4 dv = ldg_nc_v4(p.draw + pix * p.ldd + ch);
-          float a[8], b[8], c[8];
-          load_coef8(p.ca, ch, p.C, a, 0.f);
-          load_coef8(p.cb, ch, p.C, b, 0.f);
-          load_coef8(p.cc, ch, p.C, c, 0.f);
-          const uint32_t gi[4] = {gv.x, gv.y, gv.z, gv.w}, di[4] = {dv.x, dv.y, dv.z, dv.w};
-          uint32_t o[4];
+          if (p.ca == nullptr) {
+            v = gv;                                 // dd already materialised
+          } else {
+            const uint4 dv = ldg_nc_v4(p.draw + pix * p.ldd + ch);
+            float a[8], b[8], c[8];
+            load_coef8(p.ca, ch, p.C, a, 0.f);
+            load_coef8(p.cb, ch, p.C, b, 0.f);
+            load_coef8(p.cc, ch, p.C, c, 0.f);
+            const uint32_t gi[4] = {gv.x, gv.y, gv.z, gv.w}, di[4] = {dv.x, dv.y, dv.z, dv.w};
+            uint32_t o[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e)
-            o[e] = pack_bf16(fmaf(a[2 * e], bf16_lo(gi[e]), fmaf(b[2 * e], bf16_lo(di[e]), c[2 * e])),
-                             fmaf(a[2 * e + 1], bf16_hi(gi[e]), fmaf(b[2 * e + 1], bf16_hi(di[e]), c[2 * e + 1])));
-          v = make_uint4(o[0], o[1], o[2], o[3]);
+            for (int e = 0; e < 4; ++e)
+              o[e] = pack_bf16(fmaf(a[2 * e], bf16_lo(gi[e]), fmaf(b[2 * e], bf16_lo(di[e]), c[2 * e])),
+                               fmaf(a[2 * e + 1], bf16_hi(gi[e]), fmaf(b[2 * e + 1], bf16_hi(di[e]), c[2 * e + 1])));
+            v = make_uint4(o[0], o[1], o[2], o[3]);
+          }
         }
         ddt[i] = v;
       }
@@ -664,7 +682,8 @@ __global__ void dw_wgrad_reduce_kernel(const float* __restrict__ part, int rows,
 
 }  // namespace an
 
-extern "C" int an_dw_bwd_data_stats_rows(int B, int C, int H, int W, int k, int stride) {
+extern "C" int an_dw_bwd_data_stats_rows(int B, int C, int H, int W, int k, int stride, int fused) {
+  if (stride == 1 && !fused) return dw_s1_fwd_rows(B, C, H, W, k);
   return dw_bwd_data_cfg(B, C, H, W, k, stride).parts;
 }
 
@@ -673,6 +692,7 @@ extern "C" int an_dw_bwd_data(const an_dw_bwd_args* a, void* stream) {
   AN_REQUIRE(a->stride == 1 || a->stride == 2, "an_dw_bwd_data: stride %d unsupported", a->stride);
   AN_REQUIRE(a->C % 8 == 0 && a->ldg % 8 == 0 && a->ldd % 8 == 0 && a->lde % 8 == 0 && a->ldge % 8 == 0, "an_dw_bwd_data: bad layout");
   AN_REQUIRE(a->stride == 1 || (a->H % 2 == 0 && a->W % 2 == 0), "an_dw_bwd_data: stride 2 needs even H, W");
+  if (a->stride == 1 && a->ca == nullptr) return dw_s1_bwd_data(a, static_cast<cudaStream_t>(stream));
   const int P = (a->k - 1) / 2;
   const int Ho = (a->H + 2 * P - a->k) / a->stride + 1, Wo = (a->W + 2 * P - a->k) / a->stride + 1;
   const DwCfg c = dw_bwd_data_cfg(a->B, a->C, a->H, a->W, a->k, a->stride);
@@ -698,9 +718,10 @@ extern "C" int an_dw_bwd_data(const an_dw_bwd_args* a, void* stream) {
   return 2;
 }
 
-extern "C" int an_dw_bwd_weight_rows(int B, int C, int H, int W, int k, int stride) {
+extern "C" int an_dw_bwd_weight_rows(int B, int C, int H, int W, int k, int stride, int fused) {
   const int P = (k - 1) / 2;
   const int Ho = (H + 2 * P - k) / stride + 1, Wo = (W + 2 * P - k) / stride + 1;
+  if (stride == 1 && !fused) return dw_s1_wgrad_rows(B, C, H, W, k);
   return dw_bwd_weight_cfg(B, C, Ho, Wo, k, stride).ctas;
 }
 
@@ -708,6 +729,15 @@ extern "C" int an_dw_bwd_weight(const an_dw_bwd_args* a, float* partials, float*
   AN_REQUIRE(a->k == 3 || a->k == 5 || a->k == 7, "an_dw_bwd_weight: kernel size %d unsupported", a->k);
   AN_REQUIRE(a->stride == 1 || a->stride == 2, "an_dw_bwd_weight: stride %d unsupported", a->stride);
   AN_REQUIRE(a->C % 8 == 0 && partials && dw, "an_dw_bwd_weight: bad arguments");
+  if (a->stride == 1 && a->ca == nullptr && a->e_scale == nullptr) {
+    cudaStream_t s1 = static_cast<cudaStream_t>(stream);
+    if (int rc1 = dw_s1_wgrad(a, partials, s1)) return rc1;
+    const int taps1 = a->k * a->k;
+    dw_wgrad_reduce_kernel<<<(taps1 * a->C + 255) / 256, 256, 0, s1>>>(
+        partials, dw_s1_wgrad_rows(a->B, a->C, a->H, a->W, a->k), taps1, a->C, dw);
+    AN_CHECK_LAUNCH();
+    return 0;
+  }
   const int P = (a->k - 1) / 2;
   const int Ho = (a->H + 2 * P - a->k) / a->stride + 1, Wo = (a->W + 2 * P - a->k) / a->stride + 1;
   const DwWgCfg c = dw_bwd_weight_cfg(a->B, a->C, Ho, Wo, a->k, a->stride);

@@ -336,9 +336,12 @@ class Engine(object):
             if p.branches:
                 if p.expand:
                     bb.e_raw = bf16(M, p.Kh)
+                    bb.u = bf16(M, p.Kh)          # act(bn(e_raw)): the depthwise operand, TMA-staged
                     part_max = max(part_max, K.pw_gemm_stats_rows(M, p.Kh) * 2 * p.Kh)
                     wpart_max = max(wpart_max, K.pw_wgrad_splits(M, p.Kh, p.inp) * p.Kh * p.inp)
                     big_e = max(big_e, M * p.Kh)
+                else:
+                    big_e = max(big_e, M * p.inp)     # non-expanding block: du is staged in g_e
                 bb.d_raw = bf16(Mo, p.Kh)
                 if any(br.hp != br.h for br in p.branches):
                     bb.d_raw.zero_()
@@ -347,9 +350,9 @@ class Engine(object):
                 bb.p_raw = bf16(Mo, p.oup)
                 big_d = max(big_d, Mo * p.Kh)
                 for br in p.branches:
-                    part_max = max(part_max, K.dw_fwd_stats_rows(B, br.hp, ho, wo, br.k, p.stride) * 2 * br.hp,
-                                   K.dw_bwd_data_stats_rows(B, br.hp, h, w, br.k, p.stride) * 2 * br.hp)
-                    wpart_max = max(wpart_max, K.dw_bwd_weight_rows(B, br.hp, h, w, br.k, p.stride) * br.k * br.k * br.hp)
+                    part_max = max(part_max, K.dw_fwd_stats_rows(B, br.hp, ho, wo, br.k, p.stride, False) * 2 * br.hp,
+                                   K.dw_bwd_data_stats_rows(B, br.hp, h, w, br.k, p.stride, False) * 2 * br.hp)
+                    wpart_max = max(wpart_max, K.dw_bwd_weight_rows(B, br.hp, h, w, br.k, p.stride, False) * br.k * br.k * br.hp)
                 part_max = max(part_max, K.pw_gemm_stats_rows(Mo, p.oup) * 2 * p.oup,
                                K.pw_gemm_stats_rows(Mo, p.Kh) * 2 * p.Kh,
                                K.col_reduce_rows(Mo, p.oup) * 2 * p.oup)
@@ -481,17 +484,18 @@ class Engine(object):
             TAG[0] = "fwd.expand"
             K.pw_gemm(x, self.W16[p.we16:], bb.e_raw, M, p.Kh, p.inp, stats_part=stats)
             self._bn_fwd(p.bn_e, part, K.pw_gemm_stats_rows(M, p.Kh), M, training)
-            src, ld_src = bb.e_raw, p.Kh
-            e_scale, e_shift = self.bn_vec(p.bn_e, "scale"), self.bn_vec(p.bn_e, "shift")
+            # materialise the depthwise operand once (bf16): the dw kernels are FMA-issue bound and
+            # stage it with TMA, so the BN-apply + activation must not ride on their load path
+            K.affine_act(bb.e_raw, bb.u, M, p.Kh, ld1=p.Kh, ldo=p.Kh, a1=self.bn_vec(p.bn_e, "scale"),
+                         a3=self.bn_vec(p.bn_e, "shift"), act=p.act)
+            src, ld_src = bb.u, p.Kh
         else:
-            src, ld_src, e_scale, e_shift = x, p.inp, None, None
+            src, ld_src = x, p.inp
         for br in p.branches:
             TAG[0] = "fwd.dw%d" % br.k
             K.dw_fwd(src[:, br.off:], bb.d_raw[:, br.off:], self.W32[br.wd32:], B, bb.hin, bb.win, br.hp,
-                     br.k, p.stride, ldx=ld_src, ldy=p.Kh,
-                     scale=None if e_scale is None else e_scale[br.off:],
-                     shift=None if e_shift is None else e_shift[br.off:], act=p.act, stats_part=stats)
-            self._bn_fwd(p.bn_d, part, K.dw_fwd_stats_rows(B, br.hp, bb.ho, bb.wo, br.k, p.stride), Mo,
+                     br.k, p.stride, ldx=ld_src, ldy=p.Kh, act=p.act, stats_part=stats)
+            self._bn_fwd(p.bn_d, part, K.dw_fwd_stats_rows(B, br.hp, bb.ho, bb.wo, br.k, p.stride, False), Mo,
                          training, C=br.hp, off=br.off)
         TAG[0] = "fwd.project"
         K.pw_gemm(bb.d_raw, self.W16[p.wp16:], bb.p_raw, Mo, p.oup, p.Kh, a_mode=1, a_act=p.act,
@@ -597,15 +601,19 @@ class Engine(object):
                   r_scale=d_scale, r_shift=d_shift, r_mean=self.bn_vec(p.bn_d, "mean"),
                   r_rstd=self.bn_vec(p.bn_d, "rstd"), r_act=act, stats_part=part)
         self._bn_bwd(p.bn_d, part, K.pw_gemm_stats_rows(Mo, p.Kh), raw_second=True)
-        dca, dcb, dcc = (self.bn_vec(p.bn_d, n) for n in ("ca", "cb", "cc"))
+        # dd = ca*g + cb*d_raw + cc (BN-backward apply), materialised in place: both depthwise
+        # gradient kernels stage it with TMA and must not spend issue slots on the transform
+        TAG[0] = "bwd.dd"
+        K.affine_act(g_d, g_d, Mo, p.Kh, ld1=p.Kh, ldo=p.Kh, x2=bb.d_raw, ld2=p.Kh,
+                     a1=self.bn_vec(p.bn_d, "ca"), a2=self.bn_vec(p.bn_d, "cb"), a3=self.bn_vec(p.bn_d, "cc"))
         if p.expand:
-            src, ld_src = bb.e_raw, p.Kh
+            usrc, ld_src = bb.u, p.Kh              # activated input (forward operand)
             e_scale, e_shift = self.bn_vec(p.bn_e, "scale"), self.bn_vec(p.bn_e, "shift")
             e_mean, e_rstd = self.bn_vec(p.bn_e, "mean"), self.bn_vec(p.bn_e, "rstd")
-            ge, ld_ge = bf.g_e, p.Kh
+            eraw, ge, ld_ge = bb.e_raw, bf.g_e, p.Kh
         else:
-            src, ld_src, e_scale, e_shift, e_mean, e_rstd = bb.x, p.inp, None, None, None, None
-            ge, ld_ge = (dx if not p.res else bf.g_e), p.inp
+            usrc, ld_src, e_scale, e_shift, e_mean, e_rstd = bb.x, p.inp, None, None, None, None
+            eraw, ge, ld_ge = bb.x, (dx if not p.res else bf.g_e), p.inp
 
         def sl(v, br):
             return None if v is None else v[br.off:]
@@ -614,19 +622,19 @@ class Engine(object):
             o = br.off
             TAG[0] = "bwd.dw%d_wgrad" % br.k
             if br.hp == br.h:
-                K.dw_bwd_weight(g_d[o:], bb.d_raw[:, o:], src[:, o:], dca[o:], dcb[o:], dcc[o:],
-                                sl(e_scale, br), sl(e_shift, br), act if p.expand else 0, wpart,
+                K.dw_bwd_weight(g_d[o:], bb.d_raw[:, o:], usrc[:, o:], None, None, None, None, None, 0, wpart,
                                 G[br.wd_off:], B, bb.hin, bb.win, br.hp, br.k, p.stride, ldg=p.Kh, ldd=p.Kh,
                                 lde=ld_src)
             else:
-                self._dw_wgrad_padded(p, bb, br, g_d, src, ld_src, dca, dcb, dcc, e_scale, e_shift, B, wpart)
+                self._dw_wgrad_padded(p, bb, br, g_d, usrc, ld_src, B, wpart)
             TAG[0] = "bwd.dw%d_dgrad" % br.k
-            K.dw_bwd_data(g_d[o:], bb.d_raw[:, o:], src[:, o:], ge[o:], self.W32[br.wd32:], dca[o:], dcb[o:],
-                          dcc[o:], sl(e_scale, br), sl(e_shift, br), sl(e_mean, br), sl(e_rstd, br),
+            K.dw_bwd_data(g_d[o:], bb.d_raw[:, o:], eraw[:, o:], ge[o:], self.W32[br.wd32:], None, None, None,
+                          sl(e_scale, br), sl(e_shift, br), sl(e_mean, br), sl(e_rstd, br),
                           part if p.expand else None, act if p.expand else 0, B, bb.hin, bb.win, br.hp, br.k,
                           p.stride, ldg=p.Kh, ldd=p.Kh, lde=ld_src, ldge=ld_ge)
             if p.expand:
-                self._bn_bwd(p.bn_e, part, K.dw_bwd_data_stats_rows(B, br.hp, bb.hin, bb.win, br.k, p.stride),
+                self._bn_bwd(p.bn_e, part,
+                             K.dw_bwd_data_stats_rows(B, br.hp, bb.hin, bb.win, br.k, p.stride, False),
                              C=br.hp, off=o)
         if not p.expand:
             if p.res:
@@ -641,15 +649,13 @@ class Engine(object):
         K.pw_gemm(ge, self.W16[p.weT16:], dx, M, p.inp, p.Kh, x2=bb.e_raw, a_mode=2, a1=eca, a2=ecb, a3=ecc,
                   epi_mode=2, r=dy if p.res else None, ldr=p.oup)
 
-    def _dw_wgrad_padded(self, p, bb, br, g_d, src, ld_src, dca, dcb, dcc, e_scale, e_shift, B, wpart):
+    def _dw_wgrad_padded(self, p, bb, br, g_d, usrc, ld_src, B, wpart):
         """Depthwise weight gradient of a branch whose width is not a multiple of 8: run on the
         padded slot into scratch, then keep the first h rows (pad rows are exactly zero)."""
         o = br.off
         tmp = torch.empty(br.hp * br.k * br.k, device=self.dev)
-        K.dw_bwd_weight(g_d[o:], bb.d_raw[:, o:], src[:, o:], dca[o:], dcb[o:], dcc[o:],
-                        None if e_scale is None else e_scale[o:], None if e_shift is None else e_shift[o:],
-                        p.act if p.expand else 0, wpart, tmp, B, bb.hin, bb.win, br.hp, br.k, p.stride,
-                        ldg=p.Kh, ldd=p.Kh, lde=ld_src)
+        K.dw_bwd_weight(g_d[o:], bb.d_raw[:, o:], usrc[:, o:], None, None, None, None, None, 0, wpart, tmp, B,
+                        bb.hin, bb.win, br.hp, br.k, p.stride, ldg=p.Kh, ldd=p.Kh, lde=ld_src)
         n = br.h * br.k * br.k
         self.G[br.wd_off:br.wd_off + n].copy_(tmp[:n])
 

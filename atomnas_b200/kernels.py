@@ -73,8 +73,8 @@ def dw_out_hw(H, W, k, stride):
     return (H + 2 * p - k) // stride + 1, (W + 2 * p - k) // stride + 1
 
 
-def dw_fwd_stats_rows(B, C, Ho, Wo, k, stride):
-    return L.lib().an_dw_fwd_stats_rows(B, C, Ho, Wo, k, stride)
+def dw_fwd_stats_rows(B, C, Ho, Wo, k, stride, fused=True):
+    return L.lib().an_dw_fwd_stats_rows(B, C, Ho, Wo, k, stride, 1 if fused else 0)
 
 
 def dw_fwd(x, y, w, B, H, W, C, k, stride, *, ldx, ldy, scale=None, shift=None, act=0,
@@ -100,8 +100,8 @@ def _dw_bwd_args(g, draw, eraw, ge, w, ca, cb, cc, e_scale, e_shift, e_mean, e_r
     return a
 
 
-def dw_bwd_data_stats_rows(B, C, H, W, k, stride):
-    return L.lib().an_dw_bwd_data_stats_rows(B, C, H, W, k, stride)
+def dw_bwd_data_stats_rows(B, C, H, W, k, stride, fused=True):
+    return L.lib().an_dw_bwd_data_stats_rows(B, C, H, W, k, stride, 1 if fused else 0)
 
 
 def dw_bwd_data(g, draw, eraw, ge, w, ca, cb, cc, e_scale, e_shift, e_mean, e_rstd, stats_part, act,
@@ -111,8 +111,8 @@ def dw_bwd_data(g, draw, eraw, ge, w, ca, cb, cc, e_scale, e_shift, e_mean, e_rs
     L.check(L.lib().an_dw_bwd_data(a, L.stream_ptr()), "an_dw_bwd_data")
 
 
-def dw_bwd_weight_rows(B, C, H, W, k, stride):
-    return L.lib().an_dw_bwd_weight_rows(B, C, H, W, k, stride)
+def dw_bwd_weight_rows(B, C, H, W, k, stride, fused=True):
+    return L.lib().an_dw_bwd_weight_rows(B, C, H, W, k, stride, 1 if fused else 0)
 
 
 def dw_bwd_weight(g, draw, eraw, ca, cb, cc, e_scale, e_shift, act, partials, dw, B, H, W, C, k,

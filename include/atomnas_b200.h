@@ -107,6 +107,10 @@ int an_wgrad_reduce(const float* partials, int splits, int Cbig, int Csmall, int
  *             ge = du * act'(e_scale*eraw + e_shift); partials sum(ge), sum(ge*xhat_e)
  *   bwd_weight: dW[c][kr][kc] = sum dd * act(e_scale*eraw + e_shift) (master layout [C,1,k,k])
  * w is tap-major fp32 [k*k][C] (written by an_refresh_weights).
+ * Operands may be passed already materialised (scale == NULL: x is the activated input; ca == NULL:
+ * g is dd; e_scale == NULL in bwd_weight: eraw is the activated input).  Stride-1 layers with
+ * materialised operands take the TMA-staged row-streaming kernels (dw_conv_s1.cu); the `fused`
+ * flag of the *_rows helpers says which variant the partial buffers are sized for.
  * ------------------------------------------------------------------------------------------ */
 typedef struct {
   const void* x; long long ldx;
@@ -132,11 +136,11 @@ typedef struct {
 } an_dw_bwd_args;
 
 int an_dw_fwd(const an_dw_fwd_args* args, void* stream);
-int an_dw_fwd_stats_rows(int B, int C, int Ho, int Wo, int k, int stride);
+int an_dw_fwd_stats_rows(int B, int C, int Ho, int Wo, int k, int stride, int fused);
 int an_dw_bwd_data(const an_dw_bwd_args* args, void* stream);
-int an_dw_bwd_data_stats_rows(int B, int C, int H, int W, int k, int stride);
+int an_dw_bwd_data_stats_rows(int B, int C, int H, int W, int k, int stride, int fused);
 int an_dw_bwd_weight(const an_dw_bwd_args* args, float* partials, float* dw, void* stream);
-int an_dw_bwd_weight_rows(int B, int C, int H, int W, int k, int stride);
+int an_dw_bwd_weight_rows(int B, int C, int H, int W, int k, int stride, int fused);
 
 /* ------------------------------------------------------------------------------------------
  * BatchNorm2d (training mode) pieces -- nn.BatchNorm2d at models/mobilenet_base.py:142, :342.

@@ -121,7 +121,9 @@ def test_single_block_vs_bf16_point_oracle(inp, oup, stride, chans, ks, expand, 
     for n, p in blk.named_parameters():
         assert rel_l2(p.grad.cpu(), st["b." + n].grad, 1e-3 * gmax) <= 1e-2, n
     for n, b in blk.named_buffers():        # running statistics / counters
-        torch.testing.assert_close(b.cpu().float(), st["b." + n].detach().float(), rtol=1e-3, atol=1e-4)
+        torch.testing.assert_close(b.cpu().float(), st["b." + n].detach().float(), rtol=1e-3, atol=1e-4,
+                                   msg=lambda m: "%s: %s\n%s\n%s" % (n, m, b.cpu().float().flatten()[:8],
+                                                                    st["b." + n].detach().float().flatten()[:8]))
 
 
 # ------------------------------------------------------------------------------------------------

@@ -40,7 +40,7 @@ def test_library_exports_every_declared_symbol():
     # planning helpers are pure host code and must agree with themselves without a GPU
     assert handle.an_pw_gemm_stats_rows(3211264, 432) > 0
     assert handle.an_pw_wgrad_splits(3211264, 432, 24) > 0
-    assert handle.an_dw_fwd_stats_rows(256, 96, 56, 56, 7, 2) > 0
+    assert handle.an_dw_fwd_stats_rows(256, 96, 56, 56, 7, 2, 1) > 0
 
 
 def test_no_cpu_fallback():

@@ -302,3 +302,67 @@ def test_refresh_and_gather_bit_exact():
     out = torch.zeros(int(mask.sum()), 40, device=DEV)
     K.gather_rows(m.contiguous(), idx, idx.numel(), 40, out)
     assert torch.equal(out, m[mask])
+
+
+# ------------------------------------------------------------------------------------------------
+# materialised operands: stride 1 takes the TMA-staged row-streaming kernels (dw_conv_s1.cu)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,H,W,Ct,co,C,k,s", DW_CASES + [(3, 56, 56, 144, 0, 144, 7, 1), (2, 28, 28, 200, 8, 136, 5, 1)])
+def test_dw_forward_plain_operand(B, H, W, Ct, co, C, k, s):
+    torch.manual_seed(B * H + C + k + 1)
+    u = bf(torch.randn(B, H, W, Ct, device=DEV))
+    w = torch.randn(C, 1, k, k, device=DEV) * (2.0 / k / k) ** 0.5
+    Ho, Wo = K.dw_out_hw(H, W, k, s)
+    y = torch.zeros(B, Ho, Wo, Ct, device=DEV, dtype=torch.bfloat16)
+    rows = K.dw_fwd_stats_rows(B, C, Ho, Wo, k, s, fused=False)
+    part = torch.full((rows, 2, C), float("nan"), device=DEV)
+    K.dw_fwd(u[..., co:], y[..., co:], tap_major(w), B, H, W, C, k, s, ldx=Ct, ldy=Ct, stats_part=part)
+    ref = nhwc(F.conv2d(nchw(u[..., co:co + C]), w, None, s, (k - 1) // 2, 1, C))
+    got = y[..., co:co + C].float()
+    assert (got - ref).abs().max().item() <= 1e-2 * ref.abs().max().item() + 1e-3
+    if co > 0:
+        assert y[..., :co].abs().max().item() == 0
+    assert y[..., co + C:].abs().max().item() == 0 if co + C < Ct else True
+    st = part.sum(0)
+    torch.testing.assert_close(st[0], got.sum((0, 1, 2)), rtol=1e-3, atol=0.05)
+    torch.testing.assert_close(st[1], (got * got).sum((0, 1, 2)), rtol=1e-3, atol=0.05)
+
+
+@pytest.mark.parametrize("B,H,W,Ct,co,C,k,s", DW_CASES + [(3, 56, 56, 144, 0, 144, 7, 1), (2, 28, 28, 200, 8, 136, 5, 1)])
+def test_dw_backward_plain_operands(B, H, W, Ct, co, C, k, s):
+    if s == 2 and (H % 2 or W % 2):
+        pytest.skip("stride 2 needs even sizes")
+    torch.manual_seed(B + H + C + k + s + 1)
+    act = 1
+    Ho, Wo = K.dw_out_hw(H, W, k, s)
+    eraw = bf(torch.randn(B, H, W, Ct, device=DEV))
+    dd = bf(torch.randn(B, Ho, Wo, Ct, device=DEV))
+    w = torch.randn(C, 1, k, k, device=DEV) * (2.0 / k / k) ** 0.5
+    es = torch.rand(Ct, device=DEV) + 0.5
+    eh = torch.randn(Ct, device=DEV) * 0.3
+    em = torch.randn(Ct, device=DEV) * 0.1
+    er = torch.rand(Ct, device=DEV) + 0.5
+    sl = slice(co, co + C)
+    pre = es[sl] * eraw[..., sl].float() + eh[sl]
+    u = bf(act_f(es * eraw.float() + eh, act))
+    ge = torch.zeros(B, H, W, Ct, device=DEV, dtype=torch.bfloat16)
+    rows = K.dw_bwd_data_stats_rows(B, C, H, W, k, s, fused=False)
+    part = torch.full((rows, 2, C), float("nan"), device=DEV)
+    K.dw_bwd_data(dd[..., co:], dd[..., co:], eraw[..., co:], ge[..., co:], tap_major(w), None, None, None,
+                  es[co:], eh[co:], em[co:], er[co:], part, act, B, H, W, C, k, s, ldg=Ct, ldd=Ct, lde=Ct, ldge=Ct)
+    du = nhwc(torch.nn.grad.conv2d_input((B, C, H, W), w, nchw(dd[..., sl]), s, (k - 1) // 2, 1, C))
+    ref = du * act_grad(pre, act)
+    got = ge[..., sl].float()
+    assert (got - ref).abs().max().item() <= 1e-2 * ref.abs().max().item() + 1e-3
+    xh = (eraw[..., sl].float() - em[sl]) * er[sl]
+    st = part.sum(0)
+    n = B * H * W
+    torch.testing.assert_close(st[0], got.sum((0, 1, 2)), rtol=2e-3, atol=0.02 * n ** 0.5)
+    torch.testing.assert_close(st[1], (got * xh).sum((0, 1, 2)), rtol=2e-3, atol=0.02 * n ** 0.5)
+    wrows = K.dw_bwd_weight_rows(B, C, H, W, k, s, fused=False)
+    wpart = torch.full((wrows, k * k, C), float("nan"), device=DEV)
+    dw = torch.zeros(C, 1, k, k, device=DEV)
+    K.dw_bwd_weight(dd[..., co:], dd[..., co:], u[..., co:], None, None, None, None, None, 0, wpart, dw, B, H, W, C,
+                    k, s, ldg=Ct, ldd=Ct, lde=Ct)
+    wref = torch.nn.grad.conv2d_weight(nchw(u[..., sl]), (C, 1, k, k), nchw(dd[..., sl]), s, (k - 1) // 2, 1, C)
+    assert (dw - wref).abs().max().item() <= 2e-3 * wref.abs().max().item() + 1e-3
