@@ -139,13 +139,18 @@ def algorithmic_work(eng, B):
         if p.expand:
             fl = 2 * M * p.Kh * p.inp
             add(("an_pw_gemm", "fwd.expand"), 2 * (M * p.inp + M * p.Kh), fl)
+            add(("an_affine_act", "fwd.expand"), 2 * (2 * M * p.Kh), 0)          # u = act(bn(e_raw))
             add(("an_pw_wgrad", "bwd.expand_wgrad"), 2 * (2 * M * p.Kh + M * p.inp), fl)
             add(("an_pw_gemm", "bwd.expand_dgrad"), 2 * (2 * M * p.Kh + M * p.inp * (2 if p.res else 1)), fl)
         for br in p.branches:
             fl = 2 * Mo * br.hp * br.k * br.k
             add(("an_dw_fwd", "fwd.dw%d" % br.k), 2 * (M * br.hp + Mo * br.hp), fl)
-            add(("an_dw_bwd_data", "bwd.dw%d_dgrad" % br.k), 2 * (2 * Mo * br.hp + 2 * M * br.hp), fl)
-            add(("an_dw_bwd_weight", "bwd.dw%d_wgrad" % br.k), 2 * (2 * Mo * br.hp + M * br.hp), fl)
+            # dd in, activation-derivative operand (e_raw) in, g_e out
+            add(("an_dw_bwd_data", "bwd.dw%d_dgrad" % br.k), 2 * (Mo * br.hp + 2 * M * br.hp), fl)
+            add(("an_dw_bwd_weight", "bwd.dw%d_wgrad" % br.k), 2 * (Mo * br.hp + M * br.hp), fl)
+        add(("an_affine_act", "bwd.dd"), 2 * (3 * Mo * p.Kh), 0)                  # dd = ca*g + cb*d_raw + cc
+        add(("an_affine_act", "fwd.project"), 2 * (Mo * p.oup * (3 if p.res else 2)), 0)
+        add(("an_affine_act", "bwd.pw_bn"), 2 * (3 * Mo * p.oup), 0)
         fl = 2 * Mo * p.Kh * p.oup
         add(("an_pw_gemm", "fwd.project"), 2 * (Mo * p.Kh + Mo * p.oup), fl)
         add(("an_pw_wgrad", "bwd.project_wgrad"), 2 * (Mo * p.Kh + Mo * p.oup), fl)
@@ -190,22 +195,36 @@ def profile_kernels(trainer, x, y, peaks, steps=2):
 def cpu_reference(steps, warmup, batch):
     from oracle import atomnas_oracle as O
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     spec = O.NetSpec(**ATOMNAS_C_SUPERNET, input_size=IMAGE)
     ts = O.TrainState(spec, O.init_state(spec, 1995))
     g = torch.Generator().manual_seed(0)
     x = torch.randn(batch, 3, IMAGE, IMAGE, generator=g)
     y = torch.randint(0, 1000, (batch,), generator=g)
-    times = []
-    for i in range(warmup + steps):
+
+    def one():
         t0 = time.perf_counter()
         O.train_step(ts, x, y, 0.016 * 8, WEIGHT_DECAY, RHO, 0.1, 0.9999 ** 0.5)
-        if i >= warmup:
-            times.append(time.perf_counter() - t0)
+        return time.perf_counter() - t0
+
+    # thread count: the oneDNN depthwise/1x1 primitives at this batch stop scaling well before a
+    # large host's core count, so take the fastest of {all, 1/2, 1/4, 1/8} cores (one step each)
+    best_t, best_n = None, cores
+    for n in sorted({max(min(cores, 8), cores // d) for d in (16, 8, 4, 2, 1)}):
+        torch.set_num_threads(n)
+        for _ in range(max(1, warmup)):            # primitive creation per shape happens here
+            one()
+        t = one()
+        if best_t is None or t < best_t:
+            best_t, best_n = t, n
+        elif t > 1.2 * best_t:                      # past the knee (or a CPU quota): stop escalating
+            break
+    torch.set_num_threads(best_n)
+    one()
+    times = [one() for _ in range(steps)]
     sec = sum(times) / len(times)
-    return {"value": batch / sec, "unit": "images/sec", "cores": cores, "kind": "port",
-            "sample": "%d timed + %d warm-up steps of batch %d (same network, loss, optimizer; fp32, torch CPU)"
-                      % (steps, warmup, batch)}, sec
+    return {"value": batch / sec, "unit": "images/sec", "cores": best_n, "host_cores": cores, "kind": "port",
+            "sample": "%d timed steps of batch %d after warm-up (same network, loss, optimizer; fp32 torch CPU ops; "
+                      "thread count = fastest of cores/{8,4,2,1})" % (steps, batch)}, sec
 
 
 def main():
@@ -232,9 +251,10 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        base, sec = cpu_reference(min(args.steps, 3), min(warmup, 1), 16)
-        out = {"impl": "reference", "metric": "images/sec AtomNAS-C supernet fwd+bwd+RMSprop", "value": base["value"],
-               "unit": "images/sec", "n_gpus": args.gpus, "steps": min(args.steps, 3), "warmup": min(warmup, 1),
+        base, sec = cpu_reference(min(args.steps, 4), 1, 32)
+        out = {"impl": "reference", "metric": "images/sec AtomNAS-C supernet fwd+bwd+RMSprop bf16",
+               "value": base["value"],
+               "unit": "images/sec", "n_gpus": args.gpus, "steps": min(args.steps, 4), "warmup": 1,
                "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "f32", "data": "synthetic", "config": config, "cpu_baseline": base,
                "e2e": {"value": base["value"], "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -314,7 +334,7 @@ def main():
                 else "depthwise: CUDA cores, HBM roof; FMA roof reported in DESIGN.md"}
     if world == 1 and not args.no_cpu_baseline:
         try:
-            out["cpu_baseline"], _ = cpu_reference(1, 1, 16)
+            out["cpu_baseline"], _ = cpu_reference(2, 1, 32)
         except Exception as ex:                         # the baseline must never sink the GPU number
             out["cpu_baseline"] = {"error": repr(ex)}
     print(json.dumps(out))

@@ -23,7 +23,7 @@ PINNING: the reference holds no golden activation/gradient vectors (SURVEY.md se
 oracle is pinned against outputs of the reference itself, generated in the build container by
 tests/golden/make_golden.py (imports /root/reference) and committed as tests/golden/*.pt;
 tests/test_oracle_golden.py replays them.  The known-answer values of the reference's own
-unit tests (tests/utils/prune_test.py, optim_test.py) are replayed in tests/test_oracle_known.py.
+unit tests (tests/utils/prune_test.py, optim_test.py) are replayed by tests/test_oracle_golden.py::test_known_answers.
 """
 import collections
 import math
