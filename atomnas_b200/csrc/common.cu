@@ -77,12 +77,13 @@ int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_
 }
 
 int make_tmap_bf16_nhwc(CUtensorMap* tm, const void* base, uint64_t C, uint64_t W, uint64_t H,
-                        uint64_t B, uint64_t ld_elems, uint32_t box_c, uint32_t box_w, uint32_t box_h) {
+                        uint64_t B, uint64_t ld_elems, uint32_t box_c, uint32_t box_w, uint32_t box_h,
+                        uint32_t box_n) {
   EncodeTiledFn fn = encode_fn();
   AN_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled unavailable (no CUDA driver / no sm_100 GPU)");
   cuuint64_t dims[4] = {C, W, H, B};
   cuuint64_t strides[3] = {ld_elems * 2, W * ld_elems * 2, H * W * ld_elems * 2};
-  cuuint32_t box[4] = {box_c, box_w, box_h, 1};
+  cuuint32_t box[4] = {box_c, box_w, box_h, box_n};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

@@ -239,16 +239,17 @@ static int launch_dw_fwd(const DwFwdParams& p, const DwCfg& c, cudaStream_t st) 
 
 using namespace an;
 
-namespace an {   // stride-1 row-streaming kernels (dw_conv_s1.cu)
-int dw_s1_fwd_rows(int B, int C, int H, int W, int k);
-int dw_s1_wgrad_rows(int B, int C, int H, int W, int k);
-int dw_s1_fwd(const an_dw_fwd_args* a, cudaStream_t st);
-int dw_s1_bwd_data(const an_dw_bwd_args* a, cudaStream_t st);
-int dw_s1_wgrad(const an_dw_bwd_args* a, float* partials, cudaStream_t st);
+namespace an {   // row-streaming kernels for materialised operands (dw_stream.cu)
+int dw_stream_fwd_rows(int B, int C, int Ho, int Wo, int k, int stride);
+int dw_stream_dgrad_rows(int B, int C, int H, int W, int k, int stride);
+int dw_stream_wgrad_rows(int B, int C, int Ho, int Wo, int k, int stride);
+int dw_stream_fwd(const an_dw_fwd_args* a, cudaStream_t st);
+int dw_stream_bwd_data(const an_dw_bwd_args* a, cudaStream_t st);
+int dw_stream_wgrad(const an_dw_bwd_args* a, float* partials, cudaStream_t st);
 }
 
 extern "C" int an_dw_fwd_stats_rows(int B, int C, int Ho, int Wo, int k, int stride, int fused) {
-  if (stride == 1 && !fused) return dw_s1_fwd_rows(B, C, Ho, Wo, k);
+  if (!fused) return dw_stream_fwd_rows(B, C, Ho, Wo, k, stride);
   return dw_fwd_cfg(B, C, Ho, Wo, k, stride).parts;
 }
 
@@ -256,7 +257,7 @@ extern "C" int an_dw_fwd(const an_dw_fwd_args* a, void* stream) {
   AN_REQUIRE(a->k == 3 || a->k == 5 || a->k == 7, "an_dw_fwd: kernel size %d unsupported", a->k);
   AN_REQUIRE(a->stride == 1 || a->stride == 2, "an_dw_fwd: stride %d unsupported", a->stride);
   AN_REQUIRE(a->C % 8 == 0 && a->ldx % 8 == 0 && a->ldy % 8 == 0, "an_dw_fwd: channels/pitches must be multiples of 8");
-  if (a->stride == 1 && a->scale == nullptr) return dw_s1_fwd(a, static_cast<cudaStream_t>(stream));
+  if (a->scale == nullptr) return dw_stream_fwd(a, static_cast<cudaStream_t>(stream));
   const int P = (a->k - 1) / 2;
   const int Ho = (a->H + 2 * P - a->k) / a->stride + 1, Wo = (a->W + 2 * P - a->k) / a->stride + 1;
   const DwCfg c = dw_fwd_cfg(a->B, a->C, Ho, Wo, a->k, a->stride);
@@ -683,7 +684,7 @@ __global__ void dw_wgrad_reduce_kernel(const float* __restrict__ part, int rows,
 }  // namespace an
 
 extern "C" int an_dw_bwd_data_stats_rows(int B, int C, int H, int W, int k, int stride, int fused) {
-  if (stride == 1 && !fused) return dw_s1_fwd_rows(B, C, H, W, k);
+  if (!fused) return dw_stream_dgrad_rows(B, C, H, W, k, stride);
   return dw_bwd_data_cfg(B, C, H, W, k, stride).parts;
 }
 
@@ -692,7 +693,7 @@ extern "C" int an_dw_bwd_data(const an_dw_bwd_args* a, void* stream) {
   AN_REQUIRE(a->stride == 1 || a->stride == 2, "an_dw_bwd_data: stride %d unsupported", a->stride);
   AN_REQUIRE(a->C % 8 == 0 && a->ldg % 8 == 0 && a->ldd % 8 == 0 && a->lde % 8 == 0 && a->ldge % 8 == 0, "an_dw_bwd_data: bad layout");
   AN_REQUIRE(a->stride == 1 || (a->H % 2 == 0 && a->W % 2 == 0), "an_dw_bwd_data: stride 2 needs even H, W");
-  if (a->stride == 1 && a->ca == nullptr) return dw_s1_bwd_data(a, static_cast<cudaStream_t>(stream));
+  if (a->ca == nullptr) return dw_stream_bwd_data(a, static_cast<cudaStream_t>(stream));
   const int P = (a->k - 1) / 2;
   const int Ho = (a->H + 2 * P - a->k) / a->stride + 1, Wo = (a->W + 2 * P - a->k) / a->stride + 1;
   const DwCfg c = dw_bwd_data_cfg(a->B, a->C, a->H, a->W, a->k, a->stride);
@@ -721,7 +722,7 @@ extern "C" int an_dw_bwd_data(const an_dw_bwd_args* a, void* stream) {
 extern "C" int an_dw_bwd_weight_rows(int B, int C, int H, int W, int k, int stride, int fused) {
   const int P = (k - 1) / 2;
   const int Ho = (H + 2 * P - k) / stride + 1, Wo = (W + 2 * P - k) / stride + 1;
-  if (stride == 1 && !fused) return dw_s1_wgrad_rows(B, C, H, W, k);
+  if (!fused) return dw_stream_wgrad_rows(B, C, Ho, Wo, k, stride);
   return dw_bwd_weight_cfg(B, C, Ho, Wo, k, stride).ctas;
 }
 
@@ -729,12 +730,12 @@ extern "C" int an_dw_bwd_weight(const an_dw_bwd_args* a, float* partials, float*
   AN_REQUIRE(a->k == 3 || a->k == 5 || a->k == 7, "an_dw_bwd_weight: kernel size %d unsupported", a->k);
   AN_REQUIRE(a->stride == 1 || a->stride == 2, "an_dw_bwd_weight: stride %d unsupported", a->stride);
   AN_REQUIRE(a->C % 8 == 0 && partials && dw, "an_dw_bwd_weight: bad arguments");
-  if (a->stride == 1 && a->ca == nullptr && a->e_scale == nullptr) {
+  if (a->ca == nullptr && a->e_scale == nullptr) {
     cudaStream_t s1 = static_cast<cudaStream_t>(stream);
-    if (int rc1 = dw_s1_wgrad(a, partials, s1)) return rc1;
+    if (int rc1 = dw_stream_wgrad(a, partials, s1)) return rc1;
     const int taps1 = a->k * a->k;
     dw_wgrad_reduce_kernel<<<(taps1 * a->C + 255) / 256, 256, 0, s1>>>(
-        partials, dw_s1_wgrad_rows(a->B, a->C, a->H, a->W, a->k), taps1, a->C, dw);
+        partials, an_dw_bwd_weight_rows(a->B, a->C, a->H, a->W, a->k, a->stride, 0), taps1, a->C, dw);
     AN_CHECK_LAUNCH();
     return 0;
   }

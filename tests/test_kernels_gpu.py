@@ -305,9 +305,18 @@ def test_refresh_and_gather_bit_exact():
 
 
 # ------------------------------------------------------------------------------------------------
-# materialised operands: stride 1 takes the TMA-staged row-streaming kernels (dw_conv_s1.cu)
+# materialised operands: the TMA-staged row-streaming kernels (dw_stream.cu), both strides
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("B,H,W,Ct,co,C,k,s", DW_CASES + [(3, 56, 56, 144, 0, 144, 7, 1), (2, 28, 28, 200, 8, 136, 5, 1)])
+DW_REAL = [   # the AtomNAS-C layer shapes (4 / 2 / 1 columns per thread, 7 column-group warps)
+    (3, 56, 56, 144, 0, 144, 7, 1), (2, 28, 28, 200, 8, 136, 5, 1), (3, 14, 14, 480, 0, 480, 7, 1),
+    (5, 7, 7, 1152, 0, 1152, 3, 1), (9, 7, 7, 1160, 8, 1152, 7, 1), (2, 112, 112, 32, 0, 32, 3, 1),
+    (2, 112, 112, 96, 0, 96, 7, 2), (2, 56, 56, 144, 0, 144, 5, 2), (3, 28, 28, 240, 0, 240, 3, 2),
+    (3, 28, 28, 240, 0, 240, 7, 2), (5, 14, 14, 576, 0, 576, 7, 2), (5, 14, 14, 584, 8, 576, 5, 2),
+    (17, 14, 14, 96, 0, 96, 3, 1),
+]
+
+
+@pytest.mark.parametrize("B,H,W,Ct,co,C,k,s", DW_CASES + DW_REAL)
 def test_dw_forward_plain_operand(B, H, W, Ct, co, C, k, s):
     torch.manual_seed(B * H + C + k + 1)
     u = bf(torch.randn(B, H, W, Ct, device=DEV))
@@ -328,12 +337,12 @@ def test_dw_forward_plain_operand(B, H, W, Ct, co, C, k, s):
     torch.testing.assert_close(st[1], (got * got).sum((0, 1, 2)), rtol=1e-3, atol=0.05)
 
 
-@pytest.mark.parametrize("B,H,W,Ct,co,C,k,s", DW_CASES + [(3, 56, 56, 144, 0, 144, 7, 1), (2, 28, 28, 200, 8, 136, 5, 1)])
-def test_dw_backward_plain_operands(B, H, W, Ct, co, C, k, s):
+@pytest.mark.parametrize("B,H,W,Ct,co,C,k,s", DW_CASES + DW_REAL)
+@pytest.mark.parametrize("act", [1, 3])
+def test_dw_backward_plain_operands(B, H, W, Ct, co, C, k, s, act):
     if s == 2 and (H % 2 or W % 2):
         pytest.skip("stride 2 needs even sizes")
     torch.manual_seed(B + H + C + k + s + 1)
-    act = 1
     Ho, Wo = K.dw_out_hw(H, W, k, s)
     eraw = bf(torch.randn(B, H, W, Ct, device=DEV))
     dd = bf(torch.randn(B, Ho, Wo, Ct, device=DEV))
