@@ -27,11 +27,15 @@ constexpr int kTileA = kBM * kBK * 2;      // 16 KiB
 constexpr int kTileB = kMaxBN * kBK * 2;   // 16 KiB
 constexpr int kThreads = 320;
 constexpr int kMaxGroupCols = 1024;        // columns whose BN partials one CTA keeps in smem
-constexpr int kTmemCols = 256;             // 2 accumulator buffers x 128 columns
-constexpr int kAuxBytes = 256 + 4 * 2 * kMaxBN * 4 + 2 * kMaxGroupCols * 4 + kMaxBN * 8;
+constexpr int kTmemCols = 512;             // 2 x 128 accumulator columns + 128 + 16 statistics columns
+constexpr int kTmemStat1 = 256;            // D1 = Y^T Y (or G^T R): the diagonal holds the second moments
+constexpr int kTmemStat2 = 384;            // D2 = Y^T 1: column sums
+constexpr int kGroupBytes = kBM * 128;     // one staged 64-column group of an output tile: 128 rows x 128 B
+constexpr int kBarBytes = 384;
+constexpr int kAuxBytes = kBarBytes + 4 * 2 * kMaxBN * 4 + 2 * kMaxGroupCols * 4 + kMaxBN * 8;
 
 struct GemmDev {
-  CUtensorMap tm_x1, tm_x2, tm_w;
+  CUtensorMap tm_x1, tm_x2, tm_w, tm_y, tm_r;
   int M, N, K;
   int block_n, stages, m_tiles, n_tiles, tiles_per_group;
   int a_mode, a_act;
@@ -46,6 +50,8 @@ struct GemmDev {
   long long ldr;
   const float *r_scale, *r_shift, *r_mean, *r_rstd;
   int r_act;
+  // staged epilogue (bf16 output, no bias): tile -> swizzled smem -> TMA store; BN partials by MMA
+  int staged, nbuf, ytile_bytes, off_y, off_r, off_ones, off_aux;
 };
 
 // In-place prologue on one 16-byte chunk (8 channels) of a swizzled operand tile.
@@ -73,27 +79,35 @@ __device__ __forceinline__ uint4 transform_chunk(uint4 v, uint4 w, int mode, int
 
 __global__ void __launch_bounds__(kThreads, 1) pw_gemm_kernel(const __grid_constant__ GemmDev p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  // 1 KiB alignment by OFFSET (not by pointer casts): the compiler keeps the shared address space
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = p.stages;
   const int a_bytes = (p.a_mode == 2) ? 2 * kTileA : kTileA;
   const int stage_bytes = a_bytes + kTileB;
-  uint8_t* aux = smem + S * stage_bytes;
+  uint8_t* aux = smem + p.off_aux;
   uint64_t* full = reinterpret_cast<uint64_t*>(aux);
   uint64_t* xf = full + 8;
   uint64_t* empty = xf + 8;
   uint64_t* tfull = empty + 8;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  float* stat_warp = reinterpret_cast<float*>(aux + 256);   // [4][2][kMaxBN]
-  float* stat_acc = stat_warp + 4 * 2 * kMaxBN;             // [2][kMaxGroupCols]
+  uint64_t* sfull = tempty + 2;
+  uint64_t* rfull = sfull + 1;
+  uint64_t* rempty = rfull + 2;
+  uint64_t* yfull = rempty + 2;            // staged output tile written by every epilogue thread
+  uint64_t* yempty = yfull + 2;            // ... and free again (its TMA store has read it)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(yempty + 2);
+  float* stat_warp = reinterpret_cast<float*>(aux + kBarBytes);   // [4][2][kMaxBN] (direct epilogue only)
+  float* stat_acc = stat_warp + 4 * 2 * kMaxBN;                   // [2][kMaxGroupCols]
   float2* colpar = reinterpret_cast<float2*>(stat_acc + 2 * kMaxGroupCols);   // [kMaxBN]
+  const bool has_r = p.staged && p.r != nullptr && p.epi_mode != 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tm_x1);
     tma_prefetch_desc(&p.tm_w);
     if (p.a_mode == 2) tma_prefetch_desc(&p.tm_x2);
+    if (p.staged) tma_prefetch_desc(&p.tm_y);
+    if (has_r) tma_prefetch_desc(&p.tm_r);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -105,7 +119,12 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_kernel(const __grid_const
       for (int b = 0; b < 2; ++b) {
         mbar_init(&tfull[b], 1);
         mbar_init(&tempty[b], p.a_mode == 0 ? 256 : 128);
+        mbar_init(&rfull[b], 1);
+        mbar_init(&rempty[b], 1);
+        mbar_init(&yfull[b], p.a_mode == 0 ? 256 : 128);
+        mbar_init(&yempty[b], 1);
       }
+      mbar_init(sfull, 1);
       mbar_fence_init();
     }
     __syncwarp();
@@ -124,10 +143,20 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_kernel(const __grid_const
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      uint32_t it = 0;
+      uint32_t it = 0, tc = 0;
       const uint32_t tx = static_cast<uint32_t>(a_bytes + p.block_n * 128);
       for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x)
-        for (int nt = nt_begin; nt < nt_end; ++nt)
+        for (int nt = nt_begin; nt < nt_end; ++nt, ++tc) {
+          if (has_r) {                       // epilogue operand tile (saved raw tensor / residual)
+            const int rb = tc % p.nbuf;
+            const int ncol0 = nt * p.block_n;
+            const int ng = min(p.block_n / 64, (p.N - ncol0 + 63) / 64);
+            mbar_wait(&rempty[rb], ((tc / p.nbuf) & 1) ^ 1);
+            mbar_expect_tx(&rfull[rb], static_cast<uint32_t>(ng * kGroupBytes));
+            for (int gq = 0; gq < ng; ++gq)
+              tma_load_2d(smem + p.off_r + rb * p.ytile_bytes + gq * kGroupBytes, &p.tm_r, &rfull[rb],
+                          ncol0 + gq * 64, mt * kBM);
+          }
           for (int kb = 0; kb < kblocks; ++kb, ++it) {
             const int s = it % S;
             const uint32_t ph = (it / S) & 1;
@@ -138,6 +167,56 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_kernel(const __grid_const
             if (p.a_mode == 2) tma_load_2d(st + kTileA, &p.tm_x2, &full[s], kb * kBK, mt * kBM);
             tma_load_2d(st + a_bytes, &p.tm_w, &full[s], kb * kBK, nt * p.block_n);
           }
+        }
+    } else if (lane == 1 && p.staged) {
+      // -------------------------------------------------------------- tile store / statistics issuer
+      // A thread of its own (never the electing lane of a warp that also executes .sync.aligned
+      // tcgen05.ld): waits for a staged tile, issues its TMA stores and the statistics MMAs.
+      const bool want_stats = p.stats_part != nullptr;
+      uint8_t* ones = smem + p.off_ones;
+      uint32_t tc = 0;
+      for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x)
+        for (int nt = nt_begin; nt < nt_end; ++nt, ++tc) {
+          const int yb = tc % p.nbuf;
+          const uint32_t yph = (tc / p.nbuf) & 1;
+          const int ncol0 = nt * p.block_n;
+          const int ncols_valid = min(p.block_n, p.N - ncol0);
+          uint8_t* yt = smem + p.off_y + yb * p.ytile_bytes;
+          const uint8_t* rt = smem + p.off_r + yb * p.ytile_bytes;
+          mbar_wait(&yfull[yb], yph);
+          const int ng = (ncols_valid + 63) / 64;
+          for (int gq = 0; gq < ng; ++gq)
+            tma_store_2d(&p.tm_y, yt + gq * kGroupBytes, ncol0 + gq * 64, mt * kBM);
+          tma_store_commit();
+          if (want_stats) {
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(yt);
+            const uint32_t b_addr = (p.epi_mode == 1) ? smem_u32(rt) : a_addr;
+            const uint32_t o_addr = smem_u32(ones);
+            const uint32_t idesc1 = umma_idesc_bf16(128, p.block_n, 1, 1);
+            const uint32_t idesc2 = umma_idesc_bf16(128, 16, 1, 1);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)          // 16 tile rows (the contraction index) per MMA
+              umma_bf16(tmem_base + kTmemStat1, umma_desc_sw128(a_addr + k * 2048, kGroupBytes, 1024),
+                        umma_desc_sw128(b_addr + k * 2048, kGroupBytes, 1024), idesc1, k > 0 ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              umma_bf16(tmem_base + kTmemStat2, umma_desc_sw128(a_addr + k * 2048, kGroupBytes, 1024),
+                        umma_desc_sw128(o_addr + k * 2048, kGroupBytes, 1024), idesc2, k > 0 ? 1u : 0u);
+            umma_commit(sfull);
+            if (has_r) umma_commit(&rempty[yb]);           // operand tile free once the MMAs have read it
+          } else if (has_r) {
+            mbar_arrive(&rempty[yb]);                       // every epilogue thread is past its reads
+          }
+          if (p.nbuf == 2) {
+            tma_store_wait_read<1>();                       // store of the previous tile has read its smem
+            if (tc > 0) mbar_arrive(&yempty[yb ^ 1]);
+          } else {
+            tma_store_wait_read<0>();
+            mbar_arrive(&yempty[0]);
+          }
+        }
+      tma_store_wait<0>();
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
@@ -192,7 +271,10 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_kernel(const __grid_const
             const uint4 v = *ptr;
             uint4 w = make_uint4(0, 0, 0, 0);
             if (p.a_mode == 2) w = *reinterpret_cast<const uint4*>(a + i * 16 * 128 + kTileA);
-            *ptr = transform_chunk(v, w, p.a_mode, p.a_act, c1, c2, c3);
+            // rows past M were zero-filled by TMA and must stay zero (the affine shift would revive
+            // them and they would leak into the epilogue's column statistics)
+            const bool live = mt * kBM + r0 + i * 16 < p.M;
+            *ptr = live ? transform_chunk(v, w, p.a_mode, p.a_act, c1, c2, c3) : make_uint4(0, 0, 0, 0);
           }
           fence_proxy_async_smem();
           mbar_arrive(&xf[s]);
@@ -201,7 +283,7 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_kernel(const __grid_const
     // ------------------------------------------------------------------ epilogue
     // Warps 6-9 always; warps 2-5 join when there is no operand prologue (a_mode 0: exactly the
     // output-heavy GEMMs -- expand forward, projection dgrad).  Each TMEM lane quarter is then
-    // served by two warps that split the tile's 16-column chunks.
+    // served by two warps that split the tile's column chunks.
     const int nhalves = (p.a_mode == 0) ? 2 : 1;
     const int half = (warp < 6) ? 1 : 0;
     const int n_epi = 128 * nhalves;
@@ -209,42 +291,150 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_kernel(const __grid_const
     const int et = q * 32 + lane;              // row within the tile
     const int ep_tid = half * 128 + et;
     const bool want_stats = p.stats_part != nullptr;
-    const int nchunks = p.block_n / 16;
-    const int c_begin = (nhalves == 1) ? 0 : (half == 0 ? 0 : (nchunks + 1) / 2);
-    const int c_end = (nhalves == 1) ? nchunks : (half == 0 ? (nchunks + 1) / 2 : nchunks);
-    uint32_t tc = 0;
-    for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x)
-      for (int nt = nt_begin; nt < nt_end; ++nt, ++tc) {
-        const uint32_t buf = tc & 1, tph = (tc >> 1) & 1;
-        const long long row = static_cast<long long>(mt) * kBM + et;
-        const bool row_ok = row < p.M;
-        const int ncol0 = nt * p.block_n;
-        if (p.epi_mode == 1) {                 // per-column (scale, shift) of this tile -> smem
-          for (int c = ep_tid; c < p.block_n; c += n_epi) {
-            const int col = ncol0 + c;
-            colpar[c] = (col < p.N) ? make_float2(__ldg(p.r_scale + col), __ldg(p.r_shift + col))
-                                    : make_float2(0.f, 0.f);
-          }
-        }
-        uint4 rr[16];
-        if (p.epi_mode != 0) {
-#pragma unroll
-          for (int jj = 0; jj < 16; ++jj) {     // rr[k] = 8 columns starting at chunk c_begin, +8k
-            const int col = ncol0 + c_begin * 16 + jj * 8;
-            rr[jj] = make_uint4(0, 0, 0, 0);
-            if (p.r != nullptr && c_begin * 2 + jj < 2 * c_end && row_ok && col < p.N)
-              rr[jj] = ldg_nc_v4(p.r + row * p.ldr + col);
-          }
-        }
-        if (p.epi_mode == 1) named_bar_sync(1, n_epi);
-        mbar_wait(&tfull[buf], tph);
-        tc_fence_after();
-        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kMaxBN;
 
-        auto process = [&](float* v, int j, const uint4& ra, const uint4& rb) {
-          const int col0 = ncol0 + j * 16;
-          float s1[16], s2[16];
-          if (p.epi_mode == 0) {
+    if (p.staged) {
+      // ---------------- staged epilogue: TMEM -> registers -> swizzled smem tile -> TMA store.
+      // BN partial sums come from the tensor core: with the bf16 tile Y (128 rows x block_n) in
+      // shared memory as an MN-major operand, D1 = Y^T B (B = Y, or the saved raw tensor R for the
+      // backward) has the per-column second moments on its diagonal and D2 = Y^T 1 the column sums.
+      uint8_t* ones = smem + p.off_ones;
+      if (want_stats) {
+        for (int i = ep_tid; i < kGroupBytes / 16; i += n_epi)
+          reinterpret_cast<uint4*>(ones)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+        fence_proxy_async_smem();
+        named_bar_sync(1, n_epi);
+      }
+      const bool swish = p.r_act == ACT_SWISH;
+      const float lo = (p.r_act == ACT_RELU || p.r_act == ACT_RELU6) ? 0.f : -INFINITY;
+      const float hi = (p.r_act == ACT_RELU6) ? 6.f : INFINITY;
+      float4* colpar4 = reinterpret_cast<float4*>(colpar);          // per column PAIR: {s0, s1, h0, h1}
+      uint32_t tc = 0;
+      for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x)
+        for (int nt = nt_begin; nt < nt_end; ++nt, ++tc) {
+          const uint32_t buf = tc & 1, tph = (tc >> 1) & 1;
+          const int yb = tc % p.nbuf;
+          const uint32_t yph = (tc / p.nbuf) & 1;
+          const int ncol0 = nt * p.block_n;
+          const int ncols_valid = min(p.block_n, p.N - ncol0);
+          const int nchunks = (ncols_valid + 31) / 32;
+          const int c_begin = (nhalves == 1 || half == 0) ? 0 : (nchunks + 1) / 2;
+          const int c_end = (nhalves == 1) ? nchunks : (half == 0 ? (nchunks + 1) / 2 : nchunks);
+          uint8_t* yt = smem + p.off_y + yb * p.ytile_bytes;
+          const uint8_t* rt = smem + p.off_r + yb * p.ytile_bytes;
+          if (p.epi_mode == 1) {
+            for (int c = ep_tid; c < p.block_n / 2; c += n_epi) {
+              const int col = ncol0 + 2 * c;
+              colpar4[c] = (col < p.N) ? make_float4(__ldg(p.r_scale + col), __ldg(p.r_scale + col + 1),
+                                                      __ldg(p.r_shift + col), __ldg(p.r_shift + col + 1))
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            named_bar_sync(1, n_epi);
+          }
+          if (has_r) mbar_wait(&rfull[yb], yph);
+          mbar_wait(&yempty[yb], yph ^ 1);       // the store that last used this staging buffer is done
+          mbar_wait(&tfull[buf], tph);
+          tc_fence_after();
+          const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kMaxBN;
+          for (int ch = c_begin; ch < c_end; ++ch) {
+            float v[32];
+            tmem_ld32(t_row + ch * 32, v);
+            const int goff = (ch >> 1) * kGroupBytes + et * 128;
+            const int cbase = (ch & 1) * 4;                      // first 16-byte chunk of these 32 columns
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              const int phys = ((cbase + k4) ^ (et & 7)) * 16;
+              const float* vv = v + 8 * k4;
+              uint32_t o[4];
+              if (p.epi_mode == 0 || !has_r) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) o[i] = pack_bf16(vv[2 * i], vv[2 * i + 1]);
+              } else {
+                const uint4 rr = *reinterpret_cast<const uint4*>(rt + goff + phys);
+                const uint32_t ri[4] = {rr.x, rr.y, rr.z, rr.w};
+                if (p.epi_mode == 2) {
+#pragma unroll
+                  for (int i = 0; i < 4; ++i)
+                    o[i] = pack_bf16(vv[2 * i] + bf16_lo(ri[i]), vv[2 * i + 1] + bf16_hi(ri[i]));
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const float4 cpv = colpar4[ch * 16 + k4 * 4 + i];
+                    const float p0 = fmaf(cpv.x, bf16_lo(ri[i]), cpv.z);
+                    const float p1 = fmaf(cpv.y, bf16_hi(ri[i]), cpv.w);
+                    float g0, g1;
+                    if (swish) {
+                      g0 = vv[2 * i] * act_bwd(p0, ACT_SWISH);
+                      g1 = vv[2 * i + 1] * act_bwd(p1, ACT_SWISH);
+                    } else {
+                      g0 = (p0 > lo && p0 < hi) ? vv[2 * i] : 0.f;
+                      g1 = (p1 > lo && p1 < hi) ? vv[2 * i + 1] : 0.f;
+                    }
+                    o[i] = pack_bf16(g0, g1);
+                  }
+                }
+              }
+              *reinterpret_cast<uint4*>(yt + goff + phys) = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(&tempty[buf]);
+          fence_proxy_async_smem();              // tile (generic-proxy writes) -> TMA store / UMMA reads
+          mbar_arrive(&yfull[yb]);
+          if (want_stats) {
+            mbar_wait(sfull, tc & 1);
+            __syncwarp();
+            tc_fence_after();
+            const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+            const int gc = (nt - nt_begin) * p.block_n + et;
+            if (nhalves == 1 || half == 1) {                 // column sums
+              const float s1 = tmem_ld1(t_lane + kTmemStat2);
+              if (et < ncols_valid) stat_acc[gc] += s1;
+            }
+            if ((nhalves == 1 || half == 0) && q * 32 < p.block_n) {   // diagonal of D1
+              float d[32];
+              tmem_ld32(t_lane + kTmemStat1 + q * 32, d);
+#pragma unroll
+              for (int b = 16; b >= 1; b >>= 1) {
+                const bool up = (lane & b) != 0;
+#pragma unroll
+                for (int i = 0; i < b; ++i) d[i] = up ? d[i + b] : d[i];
+              }
+              if (et < ncols_valid) stat_acc[kMaxGroupCols + gc] += d[0];
+            }
+            tc_fence_before();
+          }
+        }
+      if (want_stats) {
+        named_bar_sync(1, n_epi);
+        const int gcols = (nt_end - nt_begin) * p.block_n;
+        for (int c = ep_tid; c < gcols; c += n_epi) {
+          const int col = nt_begin * p.block_n + c;
+          if (col < p.N) {
+            p.stats_part[(static_cast<long long>(blockIdx.x) * 2 + 0) * p.N + col] = stat_acc[c];
+            p.stats_part[(static_cast<long long>(blockIdx.x) * 2 + 1) * p.N + col] = stat_acc[kMaxGroupCols + c];
+          }
+        }
+      }
+    } else {
+      // ---------------- direct epilogue (fp32 output / bias: the classifier): registers -> global
+      const int nchunks = p.block_n / 16;
+      const int c_begin = (nhalves == 1) ? 0 : (half == 0 ? 0 : (nchunks + 1) / 2);
+      const int c_end = (nhalves == 1) ? nchunks : (half == 0 ? (nchunks + 1) / 2 : nchunks);
+      uint32_t tc = 0;
+      for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x)
+        for (int nt = nt_begin; nt < nt_end; ++nt, ++tc) {
+          const uint32_t buf = tc & 1, tph = (tc >> 1) & 1;
+          const long long row = static_cast<long long>(mt) * kBM + et;
+          const bool row_ok = row < p.M;
+          const int ncol0 = nt * p.block_n;
+          mbar_wait(&tfull[buf], tph);
+          tc_fence_after();
+          const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kMaxBN;
+          for (int j = c_begin; j < c_end; ++j) {
+            float v[16];
+            tmem_ld16(t_row + j * 16, v);
+            const int col0 = ncol0 + j * 16;
+            float s1[16], s2[16];
             if (p.bias != nullptr) {
 #pragma unroll
               for (int c = 0; c < 16; ++c)
@@ -260,101 +450,60 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_kernel(const __grid_const
               s1[c] = x;
               s2[c] = x * x;
             }
-          } else {
-            const uint32_t ri[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
-            float rv[16];
+            if (row_ok) {
+              if (p.y_is_f32) {
+                float* yp = reinterpret_cast<float*>(p.y) + row * p.ldy + col0;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              rv[2 * c] = bf16_lo(ri[c]);
-              rv[2 * c + 1] = bf16_hi(ri[c]);
-            }
-            if (p.epi_mode == 1) {
+                for (int g = 0; g < 4; ++g)
+                  if (col0 + g * 4 < p.N)
+                    *reinterpret_cast<float4*>(yp + g * 4) =
+                        make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+              } else {
+                __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + row * p.ldy + col0;
 #pragma unroll
-              for (int c = 0; c < 16; ++c) {
-                const float2 cpv = colpar[j * 16 + c];
-                const float pre = fmaf(cpv.x, rv[c], cpv.y);
-                const float g = (row_ok && col0 + c < p.N) ? round_bf16(v[c] * act_bwd(pre, p.r_act)) : 0.f;
-                v[c] = g;
-                s1[c] = g;
-                s2[c] = g * rv[c];           // raw second moment; the finalize kernel centres it
+                for (int g = 0; g < 2; ++g)
+                  if (col0 + g * 8 < p.N)
+                    stg_v4(yp + g * 8,
+                           make_uint4(pack_bf16(v[8 * g], v[8 * g + 1]), pack_bf16(v[8 * g + 2], v[8 * g + 3]),
+                                      pack_bf16(v[8 * g + 4], v[8 * g + 5]), pack_bf16(v[8 * g + 6], v[8 * g + 7])));
               }
-            } else {
-#pragma unroll
-              for (int c = 0; c < 16; ++c) {
-                v[c] = round_bf16(v[c] + rv[c]);
-                s1[c] = 0.f;
-                s2[c] = 0.f;
+            }
+            if (want_stats) {
+              const float t1 = warp_colsum16(s1, lane);
+              const float t2 = warp_colsum16(s2, lane);
+              if ((lane & 1) == 0) {
+                stat_warp[(q * 2 + 0) * kMaxBN + j * 16 + (lane >> 1)] = t1;
+                stat_warp[(q * 2 + 1) * kMaxBN + j * 16 + (lane >> 1)] = t2;
               }
             }
           }
-          if (row_ok) {
-            if (p.y_is_f32) {
-              float* yp = reinterpret_cast<float*>(p.y) + row * p.ldy + col0;
-#pragma unroll
-              for (int g = 0; g < 4; ++g)
-                if (col0 + g * 4 < p.N)
-                  *reinterpret_cast<float4*>(yp + g * 4) =
-                      make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
-            } else {
-              __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + row * p.ldy + col0;
-#pragma unroll
-              for (int g = 0; g < 2; ++g)
-                if (col0 + g * 8 < p.N)
-                  stg_v4(yp + g * 8,
-                         make_uint4(pack_bf16(v[8 * g], v[8 * g + 1]), pack_bf16(v[8 * g + 2], v[8 * g + 3]),
-                                    pack_bf16(v[8 * g + 4], v[8 * g + 5]), pack_bf16(v[8 * g + 6], v[8 * g + 7])));
-            }
-          }
+          tc_fence_before();
+          mbar_arrive(&tempty[buf]);
           if (want_stats) {
-            const float t1 = warp_colsum16(s1, lane);
-            const float t2 = warp_colsum16(s2, lane);
-            if ((lane & 1) == 0) {
-              stat_warp[(q * 2 + 0) * kMaxBN + j * 16 + (lane >> 1)] = t1;
-              stat_warp[(q * 2 + 1) * kMaxBN + j * 16 + (lane >> 1)] = t2;
-            }
-          }
-        };
-
+            named_bar_sync(1, n_epi);
+            if (ep_tid < p.block_n) {
+              const int gc = (nt - nt_begin) * p.block_n + ep_tid;
+              float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-        for (int jj = 0; jj < 8; jj += 2) {
-          const int j = c_begin + jj;
-          if (j + 1 < c_end) {                 // 32 accumulator columns per TMEM round trip
-            float v[32];
-            tmem_ld32(t_row + j * 16, v);
-            process(v, j, rr[2 * jj], rr[2 * jj + 1]);
-            process(v + 16, j + 1, rr[2 * jj + 2], rr[2 * jj + 3]);
-          } else if (j < c_end) {
-            float v[16];
-            tmem_ld16(t_row + j * 16, v);
-            process(v, j, rr[2 * jj], rr[2 * jj + 1]);
+              for (int w = 0; w < 4; ++w) {
+                a0 += stat_warp[(w * 2 + 0) * kMaxBN + ep_tid];
+                a1 += stat_warp[(w * 2 + 1) * kMaxBN + ep_tid];
+              }
+              stat_acc[gc] += a0;
+              stat_acc[kMaxGroupCols + gc] += a1;
+            }
+            named_bar_sync(1, n_epi);
           }
         }
-        tc_fence_before();
-        mbar_arrive(&tempty[buf]);
-        if (want_stats || p.epi_mode == 1) {
-          named_bar_sync(1, n_epi);
-          if (want_stats && ep_tid < p.block_n) {
-            const int gc = (nt - nt_begin) * p.block_n + ep_tid;
-            float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-            for (int w = 0; w < 4; ++w) {
-              a0 += stat_warp[(w * 2 + 0) * kMaxBN + ep_tid];
-              a1 += stat_warp[(w * 2 + 1) * kMaxBN + ep_tid];
-            }
-            stat_acc[gc] += a0;
-            stat_acc[kMaxGroupCols + gc] += a1;
+      if (want_stats) {
+        const int gcols = (nt_end - nt_begin) * p.block_n;
+        for (int c = ep_tid; c < gcols; c += n_epi) {
+          const int col = nt_begin * p.block_n + c;
+          if (col < p.N) {
+            p.stats_part[(static_cast<long long>(blockIdx.x) * 2 + 0) * p.N + col] = stat_acc[c];
+            p.stats_part[(static_cast<long long>(blockIdx.x) * 2 + 1) * p.N + col] =
+                stat_acc[kMaxGroupCols + c];
           }
-          named_bar_sync(1, n_epi);
-        }
-      }
-    if (want_stats) {
-      const int gcols = (nt_end - nt_begin) * p.block_n;
-      for (int c = ep_tid; c < gcols; c += n_epi) {
-        const int col = nt_begin * p.block_n + c;
-        if (col < p.N) {
-          p.stats_part[(static_cast<long long>(blockIdx.x) * 2 + 0) * p.N + col] = stat_acc[c];
-          p.stats_part[(static_cast<long long>(blockIdx.x) * 2 + 1) * p.N + col] =
-              stat_acc[kMaxGroupCols + c];
         }
       }
     }
@@ -390,8 +539,8 @@ struct WgradDev {
 __global__ void __launch_bounds__(kThreads, 1)
 pw_wgrad_kernel(const __grid_constant__ WgradDev p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  // 1 KiB alignment by OFFSET (not by pointer casts): the compiler keeps the shared address space
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = p.stages;
   const int p_bytes = (p.p_mode == 2) ? 4 * kWgBox : 2 * kWgBox;
@@ -562,8 +711,8 @@ struct GemmPlan {
 static GemmPlan plan_gemm(int M, int N) {
   GemmPlan g;
   const int sms = sm_count();
-  const int nt0 = (N + kMaxBN - 1) / kMaxBN;
-  g.block_n = (((N + nt0 - 1) / nt0) + 15) / 16 * 16;
+  // tiles are whole 64-column groups (the unit of the staged epilogue and of its TMA stores)
+  g.block_n = (N > 64) ? kMaxBN : 64;
   g.n_tiles = (N + g.block_n - 1) / g.block_n;
   g.m_tiles = (M + kBM - 1) / kBM;
   const int max_tpg = kMaxGroupCols / g.block_n;
@@ -615,7 +764,6 @@ extern "C" int an_pw_gemm(const an_pw_gemm_args* a, void* stream) {
   d.M = a->M; d.N = a->N; d.K = a->K;
   d.block_n = g.block_n; d.m_tiles = g.m_tiles; d.n_tiles = g.n_tiles;
   d.tiles_per_group = g.tiles_per_group;
-  d.stages = (a->a_mode == 2) ? 3 : 4;
   d.a_mode = a->a_mode; d.a_act = a->a_act; d.a1 = a->a1; d.a2 = a->a2; d.a3 = a->a3;
   d.epi_mode = a->epi_mode; d.y = a->y; d.ldy = a->ldy; d.y_is_f32 = a->y_is_f32;
   d.bias = a->bias; d.stats_part = a->stats_part;
@@ -623,12 +771,39 @@ extern "C" int an_pw_gemm(const an_pw_gemm_args* a, void* stream) {
   d.r_scale = a->r_scale; d.r_shift = a->r_shift; d.r_mean = a->r_mean; d.r_rstd = a->r_rstd;
   d.r_act = a->r_act;
 
+  // shared memory: [stages][output tiles][operand tiles][ones][barriers + statistics]
   const int a_bytes = (a->a_mode == 2) ? 2 * kTileA : kTileA;
-  const int smem = d.stages * (a_bytes + kTileB) + kAuxBytes + 1024;
+  const int stage_bytes = a_bytes + kTileB;
+  d.staged = (!a->y_is_f32 && a->bias == nullptr) ? 1 : 0;
+  const bool has_r = d.staged && a->r != nullptr && a->epi_mode != 0;
+  d.nbuf = (a->a_mode == 2) ? 1 : 2;
+  d.ytile_bytes = (g.block_n / 64) * kGroupBytes;
+  int fixed = 0;
+  if (d.staged) {
+    if (int e = make_tmap_bf16_2d(&d.tm_y, a->y, a->N, a->M, a->ldy, 64, kBM)) return e;
+    fixed += d.nbuf * d.ytile_bytes;
+    if (has_r) {
+      if (int e = make_tmap_bf16_2d(&d.tm_r, a->r, a->N, a->M, a->ldr, 64, kBM)) return e;
+      fixed += d.nbuf * d.ytile_bytes;
+    }
+    // statistics MMA: B operand of the column sums = one group of bf16 ones.  (Its A operand always
+    // spans two groups; with block_n = 64 the second one is whatever follows the tile -- in bounds,
+    // and only ever feeds accumulator rows that are never read.)
+    if (a->stats_part != nullptr) fixed += kGroupBytes;
+  }
+  const int budget = 227 * 1024 - 1024 - kAuxBytes - fixed;
+  d.stages = budget / stage_bytes;
+  if (d.stages > 4) d.stages = 4;
+  AN_REQUIRE(d.stages >= 2, "an_pw_gemm: shared-memory budget too small (%d B for stages)", budget);
+  d.off_y = d.stages * stage_bytes;
+  d.off_r = d.off_y + (d.staged ? d.nbuf * d.ytile_bytes : 0);
+  d.off_ones = d.off_r + (has_r ? d.nbuf * d.ytile_bytes : 0);
+  d.off_aux = d.off_ones + ((d.staged && a->stats_part != nullptr) ? kGroupBytes : 0);
+  const int smem = d.off_aux + kAuxBytes + 1024;
   static int configured = 0;
   if (configured < smem) {
-    AN_CHECK_CUDA(cudaFuncSetAttribute(pw_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = 200 * 1024;
+    AN_CHECK_CUDA(cudaFuncSetAttribute(pw_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = 227 * 1024;
   }
   dim3 grid(g.grid_x, g.groups, 1);
   pw_gemm_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(d);
