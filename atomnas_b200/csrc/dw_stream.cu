@@ -98,7 +98,8 @@ __device__ __forceinline__ void emit_row(float2 (&a)[TC], const uint32_t (&xraw)
 
 struct DwStreamParams {
   CUtensorMap tm_in;                  // streamed operand: u (forward / wgrad) or dd (data gradients)
-  CUtensorMap tm_dd;                  // wgrad only: dd rows, box {64, 4*nwc, R, ni}
+  CUtensorMap tm_dd;                  // wgrad: dd rows, box {64, TC*nwc, R, ni}; data gradients: the producer's
+                                      // raw output rows under the finishing output rows, box {64, TC*nwc, ER, ni}
   const float* w;                     // [k*k][C] tap-major fp32
   __nv_bfloat16* out;                 // forward: y; data gradient: ge
   long long ldo;
@@ -139,7 +140,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) dw_conv_stream(const __grid_co
   const int nwc = p.nwc, ni = p.ni, ncomp = nwc * ni, D = p.depth, PW = p.PW;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t img_bytes = static_cast<uint32_t>(U * PW * 128);
-  const uint32_t stage_bytes = img_bytes * ni;
+  const uint32_t in_bytes = img_bytes * ni;
+  const uint32_t e_img = (MODE != 0) ? static_cast<uint32_t>(U * TC * nwc * 128) : 0u;    // U rows of eraw
+  const uint32_t stage_bytes = in_bytes + e_img * ni;
   uint64_t* full = reinterpret_cast<uint64_t*>(dsm + (size_t)D * stage_bytes);
   uint64_t* empty = full + D;
   float* red = reinterpret_cast<float*>(empty + D);                     // [ncomp][2][64]
@@ -156,6 +159,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) dw_conv_stream(const __grid_co
     }
     mbar_fence_init();
     tma_prefetch_desc(&p.tm_in);
+    if (MODE != 0) tma_prefetch_desc(&p.tm_dd);
   }
   __syncthreads();
 
@@ -170,6 +174,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) dw_conv_stream(const __grid_co
           mbar_expect_tx(&full[st], stage_bytes);
           tma_load_4d(dsm + (size_t)st * stage_bytes, &p.tm_in, &full[st], cb0, S * ox0 - P, c * U - P,
                       (g0 + gi) * ni);
+          if (MODE != 0)          // output rows c*U-(K-1) .. c*U finish in this stage: their eraw rows
+            tma_load_4d(dsm + (size_t)st * stage_bytes + in_bytes, &p.tm_dd, &full[st], cb0, ox0, c * U - (K - 1),
+                        (g0 + gi) * ni);
         }
     }
     return;
@@ -206,6 +213,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) dw_conv_stream(const __grid_co
 
   const uint32_t* pbase = reinterpret_cast<const uint32_t*>(dsm) + (size_t)slot_img * (img_bytes / 4) +
                           (S * TC * g) * 32 + lane;
+  const uint32_t* ebase = reinterpret_cast<const uint32_t*>(dsm + in_bytes) + (size_t)slot_img * (e_img / 4) +
+                          (TC * g) * 32 + lane;
+  const int erowstride = TC * nwc * 32;
   const int rowstride = PW * 32;                                        // words
   const int oxw = ox0 + TC * g;                                         // first output column of the warp
   const bool warp_live = oxw < p.Wo;
@@ -241,11 +251,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) dw_conv_stream(const __grid_co
           uint32_t xraw[TC];
 #pragma unroll
           for (int j = 0; j < TC; ++j) xraw[j] = 0u;
-          if (MODE != 0 && e_bn && emit) {
-            const __nv_bfloat16* ep = p.eraw + (((long long)n * p.Ho + o_done) * p.Wo + oxw) * p.lde + ch;
+          if (MODE != 0 && e_bn && emit) {               // S == 1: row u of the stage's eraw box
+            const uint32_t* ep = ebase + (size_t)st * (stage_bytes / 4) + u * erowstride;
 #pragma unroll
-            for (int j = 0; j < TC; ++j)
-              if (oxw + j < p.Wo) xraw[j] = __ldg(reinterpret_cast<const unsigned int*>(ep + j * p.lde));
+            for (int j = 0; j < TC; ++j) xraw[j] = ep[j * 32];
           }
 #pragma unroll
           for (int kr = 0; kr < K; ++kr) {
@@ -314,7 +323,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) dw_dgrad2_stream(const __grid_
   const int nwc = p.nwc, ni = p.ni, ncomp = nwc * ni, D = p.depth, PW = p.PW;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t img_bytes = static_cast<uint32_t>(U * PW * 128);
-  const uint32_t stage_bytes = img_bytes * ni;
+  const uint32_t in_bytes = img_bytes * ni;
+  const uint32_t e_img = static_cast<uint32_t>(RB * TC * nwc * 128);     // the RB du rows finishing per stage
+  const uint32_t stage_bytes = in_bytes + e_img * ni;
   uint64_t* full = reinterpret_cast<uint64_t*>(dsm + (size_t)D * stage_bytes);
   uint64_t* empty = full + D;
   float* red = reinterpret_cast<float*>(empty + D);
@@ -331,6 +342,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) dw_dgrad2_stream(const __grid_
     }
     mbar_fence_init();
     tma_prefetch_desc(&p.tm_in);
+    tma_prefetch_desc(&p.tm_dd);
   }
   __syncthreads();
 
@@ -344,6 +356,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) dw_dgrad2_stream(const __grid_
           mbar_expect_tx(&full[st], stage_bytes);
           tma_load_4d(dsm + (size_t)st * stage_bytes, &p.tm_in, &full[st], cb0, ox0 / 2 + TLO, c * U + TLO,
                       (g0 + gi) * ni);
+          tma_load_4d(dsm + (size_t)st * stage_bytes + in_bytes, &p.tm_dd, &full[st], cb0, ox0,
+                      c * RB + 2 * TLO - P, (g0 + gi) * ni);
         }
     }
     return;
@@ -376,6 +390,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) dw_dgrad2_stream(const __grid_
 
   const uint32_t* pbase = reinterpret_cast<const uint32_t*>(dsm) + (size_t)slot_img * (img_bytes / 4) +
                           ((TC / 2) * g) * 32 + lane;
+  const uint32_t* ebase = reinterpret_cast<const uint32_t*>(dsm + in_bytes) + (size_t)slot_img * (e_img / 4) +
+                          (TC * g) * 32 + lane;
+  const int erowstride = TC * nwc * 32;
   const int rowstride = PW * 32;
   const int oxw = ox0 + TC * g;
   const bool warp_live = oxw < p.Wo;
@@ -410,11 +427,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) dw_dgrad2_stream(const __grid_
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
               const int y = ybase + e;
-              if (y >= 0 && y < p.Ho) {
-                const __nv_bfloat16* ep = p.eraw + (((long long)n * p.Ho + y) * p.Wo + oxw) * p.lde + ch;
+              if (y >= 0 && y < p.Ho) {                  // row 2u+e of the stage's eraw box
+                const uint32_t* ep = ebase + (size_t)st * (stage_bytes / 4) + (2 * u + e) * erowstride;
 #pragma unroll
-                for (int j = 0; j < TC; ++j)
-                  if (oxw + j < p.Wo) xraw[e][j] = __ldg(reinterpret_cast<const unsigned int*>(ep + j * p.lde));
+                for (int j = 0; j < TC; ++j) xraw[e][j] = ep[j * 32];
               }
             }
           }
@@ -629,7 +645,7 @@ static StreamCfg stream_cfg(int kind, int B, int C, int Ht, int Wt, int k, int S
     U = (k + 1) / 2;
     c.PW = (c.tc / 2) * (c.nwc - 1) + NX;
     rows = (Ht - 1 + P) / 2 - TLO + 1;                 // dd rows TLO .. floor((H-1+P)/2)
-    stage = (size_t)U * c.PW * 128 * c.ni;
+    stage = (size_t)U * c.PW * 128 * c.ni + (size_t)(k + 1) * TW * 128 * c.ni;
   } else {
     U = (S == 1) ? k : k + 1;
     const int R = (S == 1) ? k : (k + 1) / 2;
@@ -637,6 +653,7 @@ static StreamCfg stream_cfg(int kind, int B, int C, int Ht, int Wt, int k, int S
     rows = S * (Ht - 1) + k;                           // patch rows feeding Ht output rows
     stage = (size_t)U * c.PW * 128 * c.ni;
     if (kind == 1) stage += (size_t)R * TW * 128 * c.ni;
+    if (kind == 3) stage += (size_t)U * TW * 128 * c.ni;           // stride-1 data gradient: eraw rows
   }
   c.nch = (rows + U - 1) / U;
   int depth = static_cast<int>((96 * 1024) / stage);
@@ -717,7 +734,7 @@ int dw_stream_fwd_rows(int B, int C, int Ho, int Wo, int k, int stride) {
   return stream_cfg(0, B, C, Ho, Wo, k, stride).parts;
 }
 int dw_stream_dgrad_rows(int B, int C, int H, int W, int k, int stride) {
-  return stream_cfg(stride == 1 ? 0 : 2, B, C, H, W, k, stride).parts;
+  return stream_cfg(stride == 1 ? 3 : 2, B, C, H, W, k, stride).parts;
 }
 int dw_stream_wgrad_rows(int B, int C, int Ho, int Wo, int k, int stride) {
   return stream_cfg(1, B, C, Ho, Wo, k, stride).parts;
@@ -751,11 +768,13 @@ int dw_stream_fwd(const an_dw_fwd_args* a, cudaStream_t st) {
 int dw_stream_bwd_data(const an_dw_bwd_args* a, cudaStream_t st) {
   const int P = (a->k - 1) / 2, S = a->stride;
   const int Ho = (a->H + 2 * P - a->k) / S + 1, Wo = (a->W + 2 * P - a->k) / S + 1;   // dd size
-  const StreamCfg c = stream_cfg(S == 1 ? 0 : 2, a->B, a->C, a->H, a->W, a->k, S);
+  const StreamCfg c = stream_cfg(S == 1 ? 3 : 2, a->B, a->C, a->H, a->W, a->k, S);
   DwStreamParams p;
   memset(&p, 0, sizeof(p));
   const int U = (S == 1) ? a->k : (a->k + 1) / 2;
   if (int e = make_tmap_bf16_nhwc(&p.tm_in, a->g, a->C, Wo, Ho, a->B, a->ldg, 64, c.PW, U, c.ni)) return e;
+  if (int e = make_tmap_bf16_nhwc(&p.tm_dd, a->eraw, a->C, a->W, a->H, a->B, a->lde, 64, c.tc * c.nwc,
+                                  S == 1 ? a->k : a->k + 1, c.ni)) return e;
   fill_common(p, c, a->B, a->C);
   p.w = a->w;
   p.out = reinterpret_cast<__nv_bfloat16*>(a->ge); p.ldo = a->ldge;
