@@ -25,7 +25,8 @@ constexpr int kBK = 64;             // bf16 elements per 128-byte swizzle row
 constexpr int kMaxBN = 128;         // max UMMA N of the forward/dgrad kernel
 constexpr int kTileA = kBM * kBK * 2;      // 16 KiB
 constexpr int kTileB = kMaxBN * kBK * 2;   // 16 KiB
-constexpr int kThreads = 320;
+constexpr int kThreads = 320;            // weight-gradient kernel
+constexpr int kGemmThreads = 448;        // forward / dgrad kernel: + 4 more operand-prologue warps
 constexpr int kMaxGroupCols = 1024;        // columns whose BN partials one CTA keeps in smem
 constexpr int kTmemCols = 512;             // 2 x 128 accumulator columns + 128 + 16 statistics columns
 constexpr int kTmemStat1 = 256;            // D1 = Y^T Y (or G^T R): the diagonal holds the second moments
@@ -77,7 +78,7 @@ __device__ __forceinline__ uint4 transform_chunk(uint4 v, uint4 w, int mode, int
   return make_uint4(o[0], o[1], o[2], o[3]);
 }
 
-__global__ void __launch_bounds__(kThreads, 1) pw_gemm_kernel(const __grid_constant__ GemmDev p) {
+__global__ void __launch_bounds__(kGemmThreads, 1) pw_gemm_kernel(const __grid_constant__ GemmDev p) {
   extern __shared__ uint8_t smem_raw[];
   // 1 KiB alignment by OFFSET (not by pointer casts): the compiler keeps the shared address space
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_kernel(const __grid_const
     if (lane == 0) {
       for (int s = 0; s < S; ++s) {
         mbar_init(&full[s], 1);
-        mbar_init(&xf[s], 128);
+        mbar_init(&xf[s], 256);
         mbar_init(&empty[s], 1);
       }
       for (int b = 0; b < 2; ++b) {
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_kernel(const __grid_const
     __syncwarp();
     tmem_alloc(tmem_slot, kTmemCols);
   }
-  for (int i = threadIdx.x; i < 2 * kMaxGroupCols; i += kThreads) stat_acc[i] = 0.f;
+  for (int i = threadIdx.x; i < 2 * kMaxGroupCols; i += kGemmThreads) stat_acc[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -247,9 +248,11 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_kernel(const __grid_const
           }
         }
     }
-  } else if (warp < 6 && p.a_mode != 0) {
+  } else if ((warp < 6 || warp >= 10) && p.a_mode != 0) {
     // ------------------------------------------------------------------ A-operand prologue
-    const int t = threadIdx.x - 64;
+    // 8 warps (2-5 and 10-13): the K-heavy GEMMs (projection forward, expand dgrad) are bound by
+    // this in-place transform, not by their small epilogue
+    const int t = (warp < 6 ? warp - 2 : warp - 6) * 32 + lane;      // 0 .. 255
     const int cp = t & 7, r0 = t >> 3;
     const int cl = cp ^ (r0 & 7);            // logical 16B chunk held at physical chunk cp
     uint32_t it = 0;
@@ -266,20 +269,20 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_kernel(const __grid_const
           mbar_wait(&full[s], ph);
           uint8_t* a = smem + s * stage_bytes + r0 * 128 + cp * 16;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            uint4* ptr = reinterpret_cast<uint4*>(a + i * 16 * 128);
+          for (int i = 0; i < 4; ++i) {
+            uint4* ptr = reinterpret_cast<uint4*>(a + i * 32 * 128);
             const uint4 v = *ptr;
             uint4 w = make_uint4(0, 0, 0, 0);
-            if (p.a_mode == 2) w = *reinterpret_cast<const uint4*>(a + i * 16 * 128 + kTileA);
+            if (p.a_mode == 2) w = *reinterpret_cast<const uint4*>(a + i * 32 * 128 + kTileA);
             // rows past M were zero-filled by TMA and must stay zero (the affine shift would revive
             // them and they would leak into the epilogue's column statistics)
-            const bool live = mt * kBM + r0 + i * 16 < p.M;
+            const bool live = mt * kBM + r0 + i * 32 < p.M;
             *ptr = live ? transform_chunk(v, w, p.a_mode, p.a_act, c1, c2, c3) : make_uint4(0, 0, 0, 0);
           }
           fence_proxy_async_smem();
           mbar_arrive(&xf[s]);
         }
-  } else {
+  } else if (warp < 10) {
     // ------------------------------------------------------------------ epilogue
     // Warps 6-9 always; warps 2-5 join when there is no operand prologue (a_mode 0: exactly the
     // output-heavy GEMMs -- expand forward, projection dgrad).  Each TMEM lane quarter is then
@@ -806,7 +809,7 @@ extern "C" int an_pw_gemm(const an_pw_gemm_args* a, void* stream) {
     configured = 227 * 1024;
   }
   dim3 grid(g.grid_x, g.groups, 1);
-  pw_gemm_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(d);
+  pw_gemm_kernel<<<grid, kGemmThreads, smem, static_cast<cudaStream_t>(stream)>>>(d);
   AN_CHECK_LAUNCH();
   return 0;
 }
