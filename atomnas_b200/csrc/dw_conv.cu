@@ -673,12 +673,23 @@ static int launch_dw_bwd_weight(const DwBwdWeightParams& p, const DwWgCfg& c, cu
 
 // dst[c][tap] (master layout [C,1,k,k]) = sum_rows part[row][tap][c]
 __global__ void dw_wgrad_reduce_kernel(const float* __restrict__ part, int rows, int taps, int C, float* dst) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= taps * C) return;
-  const int tap = i / C, c = i % C;
+  // block = 32 consecutive (tap, channel) outputs x 8 row lanes (fixed order -> deterministic)
+  __shared__ double red[8][33];
+  const int ex = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + ex;
+  const int n = taps * C;
   double a = 0.0;
-  for (int r = 0; r < rows; ++r) a += static_cast<double>(part[((long long)r * taps + tap) * C + c]);
-  dst[(long long)c * taps + tap] = static_cast<float>(a);
+  if (i < n)
+    for (int r = rl; r < rows; r += 8) a += static_cast<double>(part[(long long)r * n + i]);
+  red[rl][ex] = a;
+  __syncthreads();
+  if (rl == 0 && i < n) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][ex];
+    const int tap = i / C, c = i % C;
+    dst[(long long)c * taps + tap] = static_cast<float>(t);
+  }
 }
 
 }  // namespace an
@@ -734,7 +745,7 @@ extern "C" int an_dw_bwd_weight(const an_dw_bwd_args* a, float* partials, float*
     cudaStream_t s1 = static_cast<cudaStream_t>(stream);
     if (int rc1 = dw_stream_wgrad(a, partials, s1)) return rc1;
     const int taps1 = a->k * a->k;
-    dw_wgrad_reduce_kernel<<<(taps1 * a->C + 255) / 256, 256, 0, s1>>>(
+    dw_wgrad_reduce_kernel<<<(taps1 * a->C + 31) / 32, 256, 0, s1>>>(
         partials, an_dw_bwd_weight_rows(a->B, a->C, a->H, a->W, a->k, a->stride, 0), taps1, a->C, dw);
     AN_CHECK_LAUNCH();
     return 0;
@@ -763,7 +774,7 @@ extern "C" int an_dw_bwd_weight(const an_dw_bwd_args* a, float* partials, float*
   }
   if (rc) return rc;
   const int taps = a->k * a->k;
-  dw_wgrad_reduce_kernel<<<(taps * a->C + 255) / 256, 256, 0, st>>>(partials, c.ctas, taps, a->C, dw);
+  dw_wgrad_reduce_kernel<<<(taps * a->C + 31) / 32, 256, 0, st>>>(partials, c.ctas, taps, a->C, dw);
   AN_CHECK_LAUNCH();
   return 0;
 }

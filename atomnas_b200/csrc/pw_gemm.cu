@@ -539,7 +539,7 @@ struct WgradDev {
   int kblocks_total, kblocks_per_split;
 };
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kGemmThreads, 1)
 pw_wgrad_kernel(const __grid_constant__ WgradDev p) {
   extern __shared__ uint8_t smem_raw[];
   // 1 KiB alignment by OFFSET (not by pointer casts): the compiler keeps the shared address space
@@ -564,7 +564,7 @@ pw_wgrad_kernel(const __grid_constant__ WgradDev p) {
     if (lane == 0) {
       for (int s = 0; s < S; ++s) {
         mbar_init(&full[s], 1);
-        mbar_init(&xf[s], 128);
+        mbar_init(&xf[s], 256);
         mbar_init(&empty[s], 1);
       }
       mbar_init(&tfull[0], 1);
@@ -625,9 +625,9 @@ pw_wgrad_kernel(const __grid_constant__ WgradDev p) {
         if (i == nkb - 1) umma_commit(&tfull[0]);
       }
     }
-  } else if (warp < 6) {
-    if (p.p_mode != 0) {
-      const int t = threadIdx.x - 64;
+  } else if (warp < 6 || warp >= 10) {
+    if (p.p_mode != 0) {               // 8 operand-prologue warps (2-5, 10-13)
+      const int t = (warp < 6 ? warp - 2 : warp - 6) * 32 + lane;
       const int cp = t & 7, r0 = t >> 3;
       const int cl = cp ^ (r0 & 7);
       float c1[2][8], c2[2][8], c3[2][8];
@@ -646,12 +646,12 @@ pw_wgrad_kernel(const __grid_constant__ WgradDev p) {
 #pragma unroll
         for (int b = 0; b < 2; ++b) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4* ptr = reinterpret_cast<uint4*>(a + b * kWgBox + j * 16 * 128);
+          for (int j = 0; j < 2; ++j) {
+            uint4* ptr = reinterpret_cast<uint4*>(a + b * kWgBox + j * 32 * 128);
             const uint4 v = *ptr;
             uint4 w = make_uint4(0, 0, 0, 0);
             if (p.p_mode == 2)
-              w = *reinterpret_cast<const uint4*>(a + (b + 2) * kWgBox + j * 16 * 128);
+              w = *reinterpret_cast<const uint4*>(a + (b + 2) * kWgBox + j * 32 * 128);
             *ptr = transform_chunk(v, w, p.p_mode, p.p_act, c1[b], c2[b], c3[b]);
           }
         }
@@ -692,15 +692,29 @@ pw_wgrad_kernel(const __grid_constant__ WgradDev p) {
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partials, int splits, int Cbig,
                                     int Csmall, int row0, int nrows, int ncols,
                                     float* __restrict__ dst, long long sb, long long ss) {
+  // block = 32 consecutive outputs x 8 split lanes (fixed summation order -> deterministic)
+  __shared__ float red[8][33];
   const long long full = static_cast<long long>(Cbig) * Csmall;
   const long long n = static_cast<long long>(nrows) * ncols;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long cb = i / ncols, cs = i % ncols;
-    const long long src = (row0 + cb) * Csmall + cs;
+  const int ex = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  for (long long base = blockIdx.x * 32LL; base < n; base += gridDim.x * 32LL) {
+    const long long i = base + ex;
     float acc = 0.f;
-    for (int s = 0; s < splits; ++s) acc += partials[s * full + src];
-    dst[cb * sb + cs * ss] = acc;
+    long long cb = 0, cs = 0;
+    if (i < n) {
+      cb = i / ncols; cs = i % ncols;
+      const long long src = (row0 + cb) * Csmall + cs;
+      for (int s = sl; s < splits; s += 8) acc += partials[s * full + src];
+    }
+    red[sl][ex] = acc;
+    __syncthreads();
+    if (sl == 0 && i < n) {
+      float a = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a += red[k][ex];
+      dst[cb * sb + cs * ss] = a;
+    }
+    __syncthreads();
   }
 }
 
@@ -875,7 +889,7 @@ extern "C" int an_pw_wgrad(const an_pw_wgrad_args* a, void* stream) {
     configured = true;
   }
   dim3 grid(w.big_blocks, w.splits, w.small_tiles);
-  pw_wgrad_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(d);
+  pw_wgrad_kernel<<<grid, kGemmThreads, smem, static_cast<cudaStream_t>(stream)>>>(d);
   AN_CHECK_LAUNCH();
   return 0;
 }
@@ -886,8 +900,8 @@ extern "C" int an_wgrad_reduce(const float* partials, int splits, int Cbig, int 
   AN_REQUIRE(partials && dst && splits > 0 && row0 >= 0 && nrows > 0 && row0 + nrows <= Cbig && ncols > 0 &&
                  ncols <= Csmall, "an_wgrad_reduce: bad arguments");
   const long long n = static_cast<long long>(nrows) * ncols;
-  int blocks = static_cast<int>((n + 255) / 256);
-  if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
+  int blocks = static_cast<int>((n + 31) / 32);
+  if (blocks > 16 * sm_count()) blocks = 16 * sm_count();
   wgrad_reduce_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(partials, splits, Cbig, Csmall, row0, nrows, ncols, dst, dst_sb, dst_ss);
   AN_CHECK_LAUNCH();
   return 0;
