@@ -26,7 +26,7 @@ tail -2 gpurun_out/${tag}_ncu_launch.log
 if [ "$2" == "full" ]; then
   # the high-resolution blocks dominate the step: the first conv launches of the forward pass and
   # the last ones of the backward pass.  T = conv launches per step, from the launch list.
-  RE='pw_gemm_kernel|pw_wgrad_kernel|dw_s1|dw_fwd|dw_bwd|affine_act'
+  RE='pw_gemm_kernel|pw_wgrad_kernel|dw_conv_stream|dw_dgrad2_stream|dw_wgrad_stream|affine_act'
   T=$(python - <<PY
 import csv, re
 rows = list(csv.reader(l for l in open("gpurun_out/${tag}_launches.csv") if l.startswith('"')))
@@ -35,10 +35,10 @@ print(sum(1 for r in rows[1:] if re.search("$RE", r[k])) // 2)
 PY
 )
   echo "conv launches per step: $T"
-  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"$RE" -c 64 \
-      -f -o /tmp/prof/${tag}_fwd python scripts/profile_step.py 256 1 > gpurun_out/${tag}_ncu_full.log 2>&1
-  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"$RE" --launch-skip $((T-110)) -c 110 \
-      -f -o /tmp/prof/${tag}_bwd python scripts/profile_step.py 256 1 >> gpurun_out/${tag}_ncu_full.log 2>&1
+  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"$RE" -c 56 \
+      -f -o /tmp/prof/${tag}_fwd python scripts/profile_step.py 64 1 > gpurun_out/${tag}_ncu_full.log 2>&1
+  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"$RE" --launch-skip $((T-100)) -c 100 \
+      -f -o /tmp/prof/${tag}_bwd python scripts/profile_step.py 64 1 >> gpurun_out/${tag}_ncu_full.log 2>&1
   tail -3 gpurun_out/${tag}_ncu_full.log
   for w in fwd bwd; do
     ncu -i /tmp/prof/${tag}_$w.ncu-rep --page raw --csv > gpurun_out/${tag}_full_$w.raw.csv 2>/dev/null
