@@ -24,6 +24,7 @@
 //   dw_wgrad_stream<K,S>   weight gradient   dW[c][kr][kc] = sum dd * u
 #include <mutex>
 #include <set>
+#include <type_traits>
 
 #include "common.cuh"
 #include "../../include/atomnas_b200.h"
@@ -229,7 +230,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) dw_conv_stream(const __grid_co
       const int st = it % D;
       mbar_wait(&full[st], (it / D) & 1);
       const uint32_t* prow = pbase + (size_t)st * (stage_bytes / 4);
-      if (live) {
+      // one stage = U patch rows.  GUARD = false is the branch-free body for stages whose rows all
+      // feed (and finish) valid output rows -- every stage of a large map except its first and last
+      auto stage_rows = [&](auto guard_tag) {
+        constexpr bool GUARD = decltype(guard_tag)::value;
         uint32_t xr[NX];
 #pragma unroll
         for (int cc = 0; cc < NX; ++cc) xr[cc] = prow[cc * 32];
@@ -243,11 +247,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) dw_conv_stream(const __grid_co
             for (int cc = 0; cc < NX; ++cc) xr[cc] = prow[(u + 1) * rowstride + cc * 32];
           }
           // output row completed by this patch row (static in u): S*o + K-1 == c*U + u
-          constexpr int dummy = 0;
-          (void)dummy;
           const bool completes = cmod(u - (K - 1), S) == 0;
           const int o_done = c * R + cfloor_div(u - (K - 1), S);
-          const bool emit = completes && o_done >= 0 && o_done < p.Ho;
+          const bool emit = completes && (!GUARD || (o_done >= 0 && o_done < p.Ho));
           uint32_t xraw[TC];
 #pragma unroll
           for (int j = 0; j < TC; ++j) xraw[j] = 0u;
@@ -262,7 +264,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) dw_conv_stream(const __grid_co
               const int dq = cfloor_div(u - kr, S);
               const int slot = cmod(dq, R);
               const int o = c * R + dq;
-              if (o >= 0 && o < p.Ho) {
+              if (!GUARD || (o >= 0 && o < p.Ho)) {
 #pragma unroll
                 for (int kc = 0; kc < K; ++kc)
 #pragma unroll
@@ -277,6 +279,12 @@ __global__ void __launch_bounds__(kMaxThreads, 1) dw_conv_stream(const __grid_co
             emit_row<TC, MODE != 0, MODE == 2>(acc[slot], xraw, op, p.ldo, ncols, es, eh, emr, er, lo, hi, st1, st2);
           }
         }
+      };
+      if (live) {
+        // every (u, kr) of the stage maps to an output row in [0, Ho)?
+        const bool interior = (c * R + cfloor_div(-(K - 1), S) >= 0) && (c * R + cfloor_div(U - 1, S) < p.Ho);
+        if (interior) stage_rows(std::false_type{});
+        else stage_rows(std::true_type{});
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[st]);
@@ -553,7 +561,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) dw_wgrad_stream(const __grid_c
         mbar_wait(&full[st], (it / D) & 1);
         const uint32_t* urow = ubase + (size_t)st * (stage_bytes / 4);
         const uint32_t* ddrow = dbase + (size_t)st * (stage_bytes / 4);
-        if (warp_live) {
+        auto stage_rows = [&](auto guard_tag) {        // GUARD = false: branch-free interior stage
+          constexpr bool GUARD = decltype(guard_tag)::value;
           uint32_t xr[NX];
 #pragma unroll
           for (int cc = 0; cc < NX; ++cc) xr[cc] = urow[cc * 32];
@@ -576,7 +585,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) dw_wgrad_stream(const __grid_c
                 const int dq = cfloor_div(u - kr, S);
                 const int slot = cmod(dq, R);
                 const int o = c * R + dq;
-                if (o >= 0 && o < p.Ho) {
+                if (!GUARD || (o >= 0 && o < p.Ho)) {
                   float2 d[TC];
 #pragma unroll
                   for (int j = 0; j < TC; ++j) d[j] = unpack2(dr[slot][j]);
@@ -589,6 +598,11 @@ __global__ void __launch_bounds__(kMaxThreads, 1) dw_wgrad_stream(const __grid_c
               }
             }
           }
+        };
+        if (warp_live) {
+          const bool interior = (c * R + cfloor_div(-(K - 1), S) >= 0) && (c * R + cfloor_div(U - 1, S) < p.Ho);
+          if (interior) stage_rows(std::false_type{});
+          else stage_rows(std::true_type{});
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[st]);

@@ -53,7 +53,6 @@ struct GemmDev {
   int r_act;
   // staged epilogue (bf16 output, no bias): tile -> swizzled smem -> TMA store; BN partials by MMA
   int staged, nbuf, ytile_bytes, off_y, off_r, off_ones, off_aux;
-  int n_outer;                        // loop order: all m tiles of an n tile first (statistics accumulate in TMEM)
 };
 
 // In-place prologue on one 16-byte chunk (8 channels) of a swizzled operand tile.
@@ -141,22 +140,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pw_gemm_kernel(const __grid_c
   const int nt_begin = blockIdx.y * p.tiles_per_group;
   const int nt_end = min(p.n_tiles, nt_begin + p.tiles_per_group);
   const int kblocks = (p.K + kBK - 1) / kBK;
-  // tiles of this CTA: m tiles blockIdx.x, +gridDim.x, ...; n tiles [nt_begin, nt_end).  n_outer walks
-  // every m tile of one n tile before the next n tile (BN partials then accumulate in TMEM).
-  const int my_mtiles = (p.m_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
-  const int my_ntiles = nt_end - nt_begin;
-  const uint32_t total_tiles = static_cast<uint32_t>(my_mtiles * my_ntiles);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       uint32_t it = 0, tc = 0;
       const uint32_t tx = static_cast<uint32_t>(a_bytes + p.block_n * 128);
-      for (tc = 0; tc < total_tiles; ++tc) {
-          const int mi = p.n_outer ? static_cast<int>(tc) % my_mtiles : static_cast<int>(tc) / my_ntiles;
-          const int ni = p.n_outer ? static_cast<int>(tc) / my_mtiles : static_cast<int>(tc) % my_ntiles;
-          const int mt = blockIdx.x + mi * gridDim.x, nt = nt_begin + ni;
-          (void)mi; (void)ni;
+      for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x)
+        for (int nt = nt_begin; nt < nt_end; ++nt, ++tc) {
           if (has_r) {                       // epilogue operand tile (saved raw tensor / residual)
             const int rb = tc % p.nbuf;
             const int ncol0 = nt * p.block_n;
@@ -185,11 +176,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pw_gemm_kernel(const __grid_c
       const bool want_stats = p.stats_part != nullptr;
       uint8_t* ones = smem + p.off_ones;
       uint32_t tc = 0;
-      for (tc = 0; tc < total_tiles; ++tc) {
-          const int mi = p.n_outer ? static_cast<int>(tc) % my_mtiles : static_cast<int>(tc) / my_ntiles;
-          const int ni = p.n_outer ? static_cast<int>(tc) / my_mtiles : static_cast<int>(tc) % my_ntiles;
-          const int mt = blockIdx.x + mi * gridDim.x, nt = nt_begin + ni;
-          (void)mi; (void)ni;
+      for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x)
+        for (int nt = nt_begin; nt < nt_end; ++nt, ++tc) {
           const int yb = tc % p.nbuf;
           const uint32_t yph = (tc / p.nbuf) & 1;
           const int ncol0 = nt * p.block_n;
@@ -208,16 +196,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pw_gemm_kernel(const __grid_c
             const uint32_t o_addr = smem_u32(ones);
             const uint32_t idesc1 = umma_idesc_bf16(128, p.block_n, 1, 1);
             const uint32_t idesc2 = umma_idesc_bf16(128, 16, 1, 1);
-            const bool keep = p.n_outer && mi > 0;           // keep accumulating over the n tile's m tiles
 #pragma unroll
             for (int k = 0; k < 8; ++k)          // 16 tile rows (the contraction index) per MMA
               umma_bf16(tmem_base + kTmemStat1, umma_desc_sw128(a_addr + k * 2048, kGroupBytes, 1024),
-                        umma_desc_sw128(b_addr + k * 2048, kGroupBytes, 1024), idesc1, (k > 0 || keep) ? 1u : 0u);
+                        umma_desc_sw128(b_addr + k * 2048, kGroupBytes, 1024), idesc1, k > 0 ? 1u : 0u);
 #pragma unroll
             for (int k = 0; k < 8; ++k)
               umma_bf16(tmem_base + kTmemStat2, umma_desc_sw128(a_addr + k * 2048, kGroupBytes, 1024),
-                        umma_desc_sw128(o_addr + k * 2048, kGroupBytes, 1024), idesc2, (k > 0 || keep) ? 1u : 0u);
-            if (!p.n_outer || mi == my_mtiles - 1) umma_commit(sfull);
+                        umma_desc_sw128(o_addr + k * 2048, kGroupBytes, 1024), idesc2, k > 0 ? 1u : 0u);
+            umma_commit(sfull);
             if (has_r) umma_commit(&rempty[yb]);           // operand tile free once the MMAs have read it
           } else if (has_r) {
             mbar_arrive(&rempty[yb]);                       // every epilogue thread is past its reads
@@ -237,11 +224,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pw_gemm_kernel(const __grid_c
     if (lane == 0) {
       uint32_t it = 0, tc = 0;
       const uint32_t idesc = umma_idesc_bf16(kBM, p.block_n, 0, 0);
-      for (tc = 0; tc < total_tiles; ++tc) {
-          const int mi = p.n_outer ? static_cast<int>(tc) % my_mtiles : static_cast<int>(tc) / my_ntiles;
-          const int ni = p.n_outer ? static_cast<int>(tc) / my_mtiles : static_cast<int>(tc) % my_ntiles;
-          const int mt = blockIdx.x + mi * gridDim.x, nt = nt_begin + ni;
-          (void)mi; (void)ni;
+      for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x)
+        for (int nt = nt_begin; nt < nt_end; ++nt, ++tc) {
           const uint32_t buf = tc & 1, tph = (tc >> 1) & 1;
           mbar_wait(&tempty[buf], tph ^ 1);
           tc_fence_after();
@@ -272,9 +256,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pw_gemm_kernel(const __grid_c
     const int cp = t & 7, r0 = t >> 3;
     const int cl = cp ^ (r0 & 7);            // logical 16B chunk held at physical chunk cp
     uint32_t it = 0;
-    for (uint32_t tq = 0; tq < total_tiles; ++tq) {
-        const int mi = p.n_outer ? static_cast<int>(tq) % my_mtiles : static_cast<int>(tq) / my_ntiles;
-        const int mt = blockIdx.x + mi * gridDim.x;
+    for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x)
+      for (int nt = nt_begin; nt < nt_end; ++nt)
         for (int kb = 0; kb < kblocks; ++kb, ++it) {
           const int s = it % S;
           const uint32_t ph = (it / S) & 1;
@@ -299,7 +282,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pw_gemm_kernel(const __grid_c
           fence_proxy_async_smem();
           mbar_arrive(&xf[s]);
         }
-    }
   } else if (warp < 10) {
     // ------------------------------------------------------------------ epilogue
     // Warps 6-9 always; warps 2-5 join when there is no operand prologue (a_mode 0: exactly the
@@ -330,11 +312,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pw_gemm_kernel(const __grid_c
       const float hi = (p.r_act == ACT_RELU6) ? 6.f : INFINITY;
       float4* colpar4 = reinterpret_cast<float4*>(colpar);          // per column PAIR: {s0, s1, h0, h1}
       uint32_t tc = 0;
-      for (tc = 0; tc < total_tiles; ++tc) {
-          const int mi = p.n_outer ? static_cast<int>(tc) % my_mtiles : static_cast<int>(tc) / my_ntiles;
-          const int ni = p.n_outer ? static_cast<int>(tc) / my_mtiles : static_cast<int>(tc) % my_ntiles;
-          const int mt = blockIdx.x + mi * gridDim.x, nt = nt_begin + ni;
-          (void)mi; (void)ni;
+      for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x)
+        for (int nt = nt_begin; nt < nt_end; ++nt, ++tc) {
           const uint32_t buf = tc & 1, tph = (tc >> 1) & 1;
           const int yb = tc % p.nbuf;
           const uint32_t yph = (tc / p.nbuf) & 1;
@@ -404,8 +383,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pw_gemm_kernel(const __grid_c
           mbar_arrive(&tempty[buf]);
           fence_proxy_async_smem();              // tile (generic-proxy writes) -> TMA store / UMMA reads
           mbar_arrive(&yfull[yb]);
-          if (want_stats && (!p.n_outer || mi == my_mtiles - 1)) {
-            mbar_wait(sfull, p.n_outer ? (ni & 1) : (tc & 1));
+          if (want_stats) {
+            mbar_wait(sfull, tc & 1);
             __syncwarp();
             tc_fence_after();
             const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
@@ -445,11 +424,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pw_gemm_kernel(const __grid_c
       const int c_begin = (nhalves == 1) ? 0 : (half == 0 ? 0 : (nchunks + 1) / 2);
       const int c_end = (nhalves == 1) ? nchunks : (half == 0 ? (nchunks + 1) / 2 : nchunks);
       uint32_t tc = 0;
-      for (tc = 0; tc < total_tiles; ++tc) {
-          const int mi = p.n_outer ? static_cast<int>(tc) % my_mtiles : static_cast<int>(tc) / my_ntiles;
-          const int ni = p.n_outer ? static_cast<int>(tc) / my_mtiles : static_cast<int>(tc) % my_ntiles;
-          const int mt = blockIdx.x + mi * gridDim.x, nt = nt_begin + ni;
-          (void)mi; (void)ni;
+      for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x)
+        for (int nt = nt_begin; nt < nt_end; ++nt, ++tc) {
           const uint32_t buf = tc & 1, tph = (tc >> 1) & 1;
           const long long row = static_cast<long long>(mt) * kBM + et;
           const bool row_ok = row < p.M;
@@ -840,9 +816,6 @@ extern "C" int an_pw_gemm(const an_pw_gemm_args* a, void* stream) {
   d.off_r = d.off_y + (d.staged ? d.nbuf * d.ytile_bytes : 0);
   d.off_ones = d.off_r + (has_r ? d.nbuf * d.ytile_bytes : 0);
   d.off_aux = d.off_ones + ((d.staged && a->stats_part != nullptr) ? kGroupBytes : 0);
-  // n-outer order (statistics accumulated in TMEM over an n tile's m tiles) measured SLOWER on B200:
-  // a row's column ranges are then written far apart in time (4.9 vs 3.5 ms for the expand GEMMs)
-  d.n_outer = 0;
   const int smem = d.off_aux + kAuxBytes + 1024;
   static int configured = 0;
   if (configured < smem) {

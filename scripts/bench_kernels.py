@@ -104,6 +104,8 @@ def pw_sweep(B, out):
         z = torch.zeros(Kh, device=DEV)
         ms = timeit(lambda i: K.pw_gemm(x[i], we, e[i], M, Kh, cin, stats_part=part), nr)
         rows = [("pw_expand_fwd", ms, 2 * M * (cin + Kh), M, Kh, cin)]
+        ms = timeit(lambda i: K.pw_gemm(x[i], we, e[i], M, Kh, cin), nr)       # store-only ceiling of the epilogue
+        rows.append(("pw_expand_fwd_nostats", ms, 2 * M * (cin + Kh), M, Kh, cin))
         # expand dgrad: a_mode 2 on (g_e, e_raw): [M, Kh] x [cin, Kh]^T -> dx [M, cin]
         ms = timeit(lambda i: K.pw_gemm(e[i], weT, x[i], M, cin, Kh, x2=e[(i + 1) % nr], a_mode=2, a1=v, a2=z, a3=z), nr)
         rows.append(("pw_expand_dgrad", ms, 2 * M * (2 * Kh + cin), M, cin, Kh))
