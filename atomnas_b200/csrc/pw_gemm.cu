@@ -114,15 +114,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pw_gemm_kernel(const __grid_c
     if (lane == 0) {
       for (int s = 0; s < S; ++s) {
         mbar_init(&full[s], 1);
-        mbar_init(&xf[s], 256);
+        mbar_init(&xf[s], 8);                  // one elected arrival per prologue warp
         mbar_init(&empty[s], 1);
       }
       for (int b = 0; b < 2; ++b) {
         mbar_init(&tfull[b], 1);
-        mbar_init(&tempty[b], p.a_mode == 0 ? 256 : 128);
+        mbar_init(&tempty[b], p.a_mode == 0 ? 8 : 4);   // one elected arrival per epilogue warp
         mbar_init(&rfull[b], 1);
         mbar_init(&rempty[b], 1);
-        mbar_init(&yfull[b], p.a_mode == 0 ? 256 : 128);
+        mbar_init(&yfull[b], p.a_mode == 0 ? 8 : 4);
         mbar_init(&yempty[b], 1);
       }
       mbar_init(sfull, 1);
@@ -280,7 +280,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pw_gemm_kernel(const __grid_c
             *ptr = live ? transform_chunk(v, w, p.a_mode, p.a_act, c1, c2, c3) : make_uint4(0, 0, 0, 0);
           }
           fence_proxy_async_smem();
-          mbar_arrive(&xf[s]);
+          __syncwarp();                          // 256 per-thread arrivals on one mbarrier serialise
+          if (lane == 0) mbar_arrive(&xf[s]);
         }
   } else if (warp < 10) {
     // ------------------------------------------------------------------ epilogue
@@ -338,9 +339,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pw_gemm_kernel(const __grid_c
           mbar_wait(&tfull[buf], tph);
           tc_fence_after();
           const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kMaxBN;
+          if (c_begin >= c_end) {                // ragged tile: nothing to drain for this half
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[buf]);
+          }
           for (int ch = c_begin; ch < c_end; ++ch) {
             float v[32];
             tmem_ld32(t_row + ch * 32, v);
+            if (ch == c_end - 1) {               // accumulator is in registers: free it for the next MMA
+              tc_fence_before();                 // before the (slower) staging of this chunk
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tempty[buf]);
+            }
             const int goff = (ch >> 1) * kGroupBytes + et * 128;
             const int cbase = (ch & 1) * 4;                      // first 16-byte chunk of these 32 columns
 #pragma unroll
@@ -379,10 +390,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pw_gemm_kernel(const __grid_c
               *reinterpret_cast<uint4*>(yt + goff + phys) = make_uint4(o[0], o[1], o[2], o[3]);
             }
           }
-          tc_fence_before();
-          mbar_arrive(&tempty[buf]);
           fence_proxy_async_smem();              // tile (generic-proxy writes) -> TMA store / UMMA reads
-          mbar_arrive(&yfull[yb]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&yfull[yb]);     // one arrival per warp: per-thread arrivals serialise
           if (want_stats) {
             mbar_wait(sfull, tc & 1);
             __syncwarp();
@@ -481,7 +491,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pw_gemm_kernel(const __grid_c
             }
           }
           tc_fence_before();
-          mbar_arrive(&tempty[buf]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[buf]);
           if (want_stats) {
             named_bar_sync(1, n_epi);
             if (ep_tid < p.block_n) {
@@ -564,7 +575,7 @@ pw_wgrad_kernel(const __grid_constant__ WgradDev p) {
     if (lane == 0) {
       for (int s = 0; s < S; ++s) {
         mbar_init(&full[s], 1);
-        mbar_init(&xf[s], 256);
+        mbar_init(&xf[s], 8);                  // one elected arrival per prologue warp
         mbar_init(&empty[s], 1);
       }
       mbar_init(&tfull[0], 1);
@@ -656,7 +667,8 @@ pw_wgrad_kernel(const __grid_constant__ WgradDev p) {
           }
         }
         fence_proxy_async_smem();
-        mbar_arrive(&xf[s]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&xf[s]);
       }
     }
   } else {
