@@ -52,6 +52,9 @@ long long an_launch_count(void);
  *               centres the second moment)
  *   epi_mode 2: y = D + r                             (residual gradient add; r may be NULL)
  * stats_part, when not NULL, receives an_pw_gemm_stats_rows(M,N) rows of [2][N] floats.
+ * bf16 outputs without bias leave through a staged epilogue (TMEM -> swizzled smem -> TMA store)
+ * and their partials are computed by the tensor core from the staged bf16 tile (diag(Y^T Y), Y^T 1);
+ * fp32 output / bias (the classifier) takes the direct register -> global epilogue.
  * ------------------------------------------------------------------------------------------ */
 typedef struct {
   const void* x1; long long ldx1;
@@ -108,9 +111,10 @@ int an_wgrad_reduce(const float* partials, int splits, int Cbig, int Csmall, int
  *   bwd_weight: dW[c][kr][kc] = sum dd * act(e_scale*eraw + e_shift) (master layout [C,1,k,k])
  * w is tap-major fp32 [k*k][C] (written by an_refresh_weights).
  * Operands may be passed already materialised (scale == NULL: x is the activated input; ca == NULL:
- * g is dd; e_scale == NULL in bwd_weight: eraw is the activated input).  Stride-1 layers with
- * materialised operands take the TMA-staged row-streaming kernels (dw_conv_s1.cu); the `fused`
- * flag of the *_rows helpers says which variant the partial buffers are sized for.
+ * g is dd; e_scale == NULL in bwd_weight: eraw is the activated input).  Materialised operands
+ * (both strides) take the TMA-staged row-streaming kernels (csrc/dw_stream.cu) -- the engine's hot
+ * path; the on-load transforms run on the tile kernels (csrc/dw_conv.cu).  The `fused` flag of the
+ * *_rows helpers says which variant the partial buffers are sized for (fused = 0: materialised).
  * ------------------------------------------------------------------------------------------ */
 typedef struct {
   const void* x; long long ldx;
