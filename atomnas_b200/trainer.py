@@ -127,14 +127,50 @@ class Trainer(object):
         self._graph.replay()
         return out
 
-    def step_host(self, x_host, y_host, rho=0.0, lr=None):
-        """End-to-end step from (pinned) host buffers: H2D copies, the step, mean loss (device)."""
-        if self._x_dev is None or self._x_dev.shape != x_host.shape:
-            self._x_dev = torch.empty(x_host.shape, device=self.eng.dev, dtype=torch.float32)
-            self._y_dev = torch.empty(y_host.shape, device=self.eng.dev, dtype=torch.int64)
-        self._x_dev.copy_(x_host, non_blocking=True)
-        self._y_dev.copy_(y_host, non_blocking=True)
-        return self.step(self._x_dev, self._y_dev, rho, lr).mean()
+    def step_host(self, x_host, y_host, rho=0.0, lr=None, prefetch=None):
+        """End-to-end step from (pinned) host buffers: H2D copies, the step, mean loss (device).
+
+        prefetch=(x_next, y_next) starts the NEXT batch's host->device copies on a side stream
+        while this step computes, into the other of two device buffers -- the double-buffered
+        side-stream input pipeline of the reference's DataPrefetcher (utils/dataflow.py:13-58).
+        A later step_host call with those same host tensors picks the prefetched buffer up."""
+        dev = self.eng.dev
+        if self._x_dev is None or self._x_dev[0].shape != x_host.shape:
+            self._x_dev = [torch.empty(x_host.shape, device=dev, dtype=torch.float32) for _ in range(2)]
+            self._y_dev = [torch.empty(y_host.shape, device=dev, dtype=torch.int64) for _ in range(2)]
+            self._pf_key, self._pf_slot = None, 0
+            self._pf_ready = [None, None]          # copy finished (recorded on the copy stream)
+            self._consumed = [None, None]          # step that read the buffer finished (compute stream)
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        cur = torch.cuda.current_stream()
+        key = (x_host.data_ptr(), y_host.data_ptr(), tuple(x_host.shape))
+        if self._pf_key == key and self._pf_ready[self._pf_slot] is not None:
+            slot = self._pf_slot
+            cur.wait_event(self._pf_ready[slot])
+        else:                                      # not prefetched: copy on the compute stream
+            slot = 1 - self._pf_slot
+            self._x_dev[slot].copy_(x_host, non_blocking=True)
+            self._y_dev[slot].copy_(y_host, non_blocking=True)
+        self._pf_key = None
+        loss = self.step(self._x_dev[slot], self._y_dev[slot], rho, lr)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self._consumed[slot] = ev
+        if prefetch is not None:
+            xn, yn = prefetch
+            other = 1 - slot
+            cs = self._copy_stream
+            if self._consumed[other] is not None:
+                cs.wait_event(self._consumed[other])
+            with torch.cuda.stream(cs):
+                self._x_dev[other].copy_(xn, non_blocking=True)
+                self._y_dev[other].copy_(yn, non_blocking=True)
+                rdy = torch.cuda.Event()
+                rdy.record(cs)
+            self._pf_ready[other] = rdy
+            self._pf_key = (xn.data_ptr(), yn.data_ptr(), tuple(xn.shape))
+            self._pf_slot = other
+        return loss.mean()
 
     def reg_losses(self, rho):
         """(l2, l1) regularisation loss values for logging (train.py:203-208)."""

@@ -294,7 +294,8 @@ def main():
     last = [None]
 
     def e2e_step():
-        last[0] = trainer.step_host(x_host, y_host, rho=RHO).item()
+        # the next batch's H2D copy runs on a side stream under this step (DataPrefetcher pattern)
+        last[0] = trainer.step_host(x_host, y_host, rho=RHO, prefetch=(x_host, y_host)).item()
 
     for _ in range(2):
         e2e_step()
