@@ -41,6 +41,27 @@ def test_library_exports_every_declared_symbol():
     assert handle.an_pw_gemm_stats_rows(3211264, 432) > 0
     assert handle.an_pw_wgrad_splits(3211264, 432, 24) > 0
     assert handle.an_dw_fwd_stats_rows(256, 96, 56, 56, 7, 2, 1) > 0
+    # every AtomNAS-C depthwise shape has a streaming-kernel plan (materialised operands, fused = 0)
+    for C, H, s in [(32, 112, 1), (96, 112, 2), (144, 56, 1), (144, 56, 2), (240, 28, 1), (240, 28, 2),
+                    (480, 14, 1), (576, 14, 1), (576, 14, 2), (1152, 7, 1)]:
+        for k in (3, 5, 7):
+            ho = H // s
+            assert handle.an_dw_fwd_stats_rows(256, C, ho, ho, k, s, 0) > 0
+            assert handle.an_dw_bwd_data_stats_rows(256, C, H, H, k, s, 0) > 0
+            assert handle.an_dw_bwd_weight_rows(256, C, H, H, k, s, 0) > 0
+
+
+def test_header_prototypes_match_ctypes_signatures():
+    """Argument counts of include/atomnas_b200.h and of the ctypes binding must agree (an ABI drift
+    between the two would corrupt the stack silently)."""
+    header = open(os.path.join(ROOT, "include", "atomnas_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    protos = dict(re.findall(r"\b(an_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S))
+    assert set(protos) == set(L.SIGNATURES)
+    for name, args in protos.items():
+        args = args.strip()
+        n = 0 if args in ("", "void") else len([a for a in args.split(",") if a.strip()])
+        assert n == len(L.SIGNATURES[name][1]), (name, n, len(L.SIGNATURES[name][1]))
 
 
 def test_no_cpu_fallback():
