@@ -202,3 +202,60 @@ def test_data_parallel_helpers_gloo_world2():
     assert torch.allclose(a[3], torch.arange(8, 13, dtype=torch.float32) * 1.5)
     assert torch.allclose(a[4], torch.full((5,), 1.5))
     assert a[5] is True and b[5] is False and a[6] == 2
+
+
+_DROPIN_PROBE = r'''
+import importlib, json, os, sys
+os.chdir(sys.argv[1])
+os.environ.setdefault("ARNOLD_OUTPUT", "/tmp/an_out")
+os.environ.setdefault("DATA_LMDB", "/tmp/an_data")
+sys.argv = ["train.py", "app:apps/slimming/shrink/atomnas_c.yml"]
+from utils.config import FLAGS                      # always the REFERENCE's config loader
+m = importlib.import_module(FLAGS.model)             # common.py:129-130
+model = m.Model(**FLAGS.model_kwparams, input_size=FLAGS.image_size)
+out = {"model_module": type(model).__module__,
+       "keys": [[k, list(v.shape)] for k, v in model.state_dict().items()],
+       "blocks": list(model.get_named_block_list().keys()),
+       "rmsprop": importlib.import_module("utils.rmsprop").RMSprop.__module__,
+       "ema": importlib.import_module("utils.optim").ExponentialMovingAverage.__module__,
+       "prune": importlib.import_module("utils.prune").get_bn_to_prune.__module__,
+       "dist": importlib.import_module("utils.distributed").allreduce_grads.__module__,
+       "config": importlib.import_module("utils.config").__file__}
+print("RESULT " + json.dumps(out))
+'''
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/apps"), reason="reference checkout not present")
+def test_dropin_shims_build_the_yaml_model_like_the_reference():
+    """train.py's model factory (common.py:129-130) on the UNCHANGED atomnas_c.yml: with dropin/ first
+    on sys.path the reference's config loader and YAML produce OUR module tree, with exactly the
+    reference's state_dict keys and shapes; the optimizer / EMA / prune / distributed imports resolve
+    to this repo while utils.config still is the reference's file."""
+    import json
+    import subprocess
+    ref = "/root/reference"
+
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        script = os.path.join(tmp, "probe_train.py")      # stands in for train.py (same imports, same factory)
+        with open(script, "w") as f:
+            f.write(_DROPIN_PROBE)
+
+        def probe(cmd, env_extra):
+            env = dict(os.environ, **env_extra)
+            r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+            lines = [ln for ln in r.stdout.splitlines() if ln.startswith("RESULT ")]
+            assert lines, r.stderr[-2000:]
+            return json.loads(lines[-1][7:])
+
+        # through the launcher: dropin/ first, whatever directory the script lives in
+        ours = probe([sys.executable, os.path.join(ROOT, "dropin", "launch.py"), script, ref],
+                     {"ATOMNAS_REFERENCE": ref, "PYTHONPATH": ""})
+        theirs = probe([sys.executable, script, ref], {"PYTHONPATH": ref})
+    assert ours["model_module"] == "atomnas_b200.mobilenet_supernet"
+    assert theirs["model_module"] == "models.mobilenet_supernet"
+    assert ours["keys"] == theirs["keys"]
+    assert ours["blocks"] == theirs["blocks"]
+    for k in ("rmsprop", "ema", "prune", "dist"):
+        assert ours[k].startswith("atomnas_b200."), (k, ours[k])
+    assert ours["config"].startswith(ref)
