@@ -1,5 +1,5 @@
 import os, sys, torch, collections
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from atomnas_b200 import mobilenet_base as mb
 from oracle import atomnas_oracle as O

@@ -4,7 +4,7 @@ the GPU box, so this runs the oracle's functional restatement of it (identical F
 F.batch_norm / autograd calls, Python-loop RMSprop + EMA as in train.py) on CUDA tensors.
 Not part of the product or of bench.py's contract; prints one JSON line per mode.
 
-    python scripts/ref_gpu_eager.py [batch] [steps]
+    python tests/tools/ref_gpu_eager.py [batch] [steps]
 """
 import json
 import os
@@ -13,7 +13,7 @@ import time
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 from oracle import atomnas_oracle as O  # noqa: E402
