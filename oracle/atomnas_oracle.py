@@ -11,6 +11,8 @@ F.conv2d / F.batch_norm primitives and follows the reference's module code for t
 
   network       models/mobilenet_supernet.py:58-173, models/searched_network.py:14-144
   block         models/mobilenet_base.py:277-382 (InvertedResidualChannels), :120-142 (ConvBNReLU)
+  fused/SE blk  models/mobilenet_base.py:145-268 (InvertedResidualChannelsFused), :93-117 (SE) -- the
+                next scope row (8f-1); restated and pinned ahead of its kernels
   activations   models/mobilenet_base.py:407-415
   init          models/mobilenet_base.py:440-459 (init_weights_mnas)
   loss          utils/optim.py:180-207 (CrossEntropyLabelSmooth), :210-249 (cal_l2_loss 'mnas'),
@@ -208,6 +210,44 @@ def _bn(spec, st, name, x, training):
 def _conv_bn_act(spec, st, name, x, stride, groups, training, k):
     x = F.conv2d(x, st[name + ".0.weight"], None, stride, (k - 1) // 2, 1, groups)
     return act(_bn(spec, st, name + ".1", x, training), spec.active_fn)
+
+
+def fused_block_forward(spec, st, name, x, inp, oup, stride, channels, kernel_sizes, expand,
+                        se_ratio=None, training=True):
+    """InvertedResidualChannelsFused.forward (models/mobilenet_base.py:258-268) with the optional
+    SqueezeAndExcitation (:93-112) -- the block of the searched AtomNAS-C+ nets (scope table 8f-1).
+
+    One expand conv over the concatenated hidden width (:186-193), each depthwise branch on its
+    narrow slice (:196-216), concat, SE gate = sigmoid(expand(act(reduce(mean_HW(t))))) with biased
+    1x1 convs of widths hidden_total -> round(inp * se_ratio) -> hidden_total (:225-230, :109-112),
+    linear projection + BN (:217-219), residual iff stride == 1 and inp == oup (:171).
+    State names are the reference's: {name}.expand_conv.{0,1}, .depth_ops.{i}.{idx}.{0,1} (idx = 1
+    behind the Narrow when expanding), .se_op.se_reduce / .se_expand, .project_conv.{0,1}."""
+    t = x
+    if expand:
+        t = _conv_bn_act(spec, st, name + ".expand_conv", t, 1, 1, training, 1)
+    outs, start = [], 0
+    for i, (h, k) in enumerate(zip(channels, kernel_sizes)):
+        if expand:
+            u = t.narrow(1, start, h)
+            start += h
+            base = "%s.depth_ops.%d.1" % (name, i)
+        else:
+            u = t
+            base = "%s.depth_ops.%d.0" % (name, i)
+        outs.append(_conv_bn_act(spec, st, base, u, stride, h, training, k))
+    t = outs[0] if len(outs) == 1 else torch.cat(outs, 1)
+    if se_ratio is not None:
+        g = t.mean((2, 3), keepdim=True)
+        g = F.conv2d(g, st[name + ".se_op.se_reduce.weight"], st[name + ".se_op.se_reduce.bias"])
+        g = F.conv2d(act(g, spec.active_fn), st[name + ".se_op.se_expand.weight"],
+                     st[name + ".se_op.se_expand.bias"])
+        t = torch.sigmoid(g) * t
+    t = F.conv2d(t, st[name + ".project_conv.0.weight"])
+    t = _bn(spec, st, name + ".project_conv.1", t, training)
+    if stride == 1 and inp == oup:
+        return x + t
+    return t
 
 
 def block_forward(spec, st, b, x, training=True):

@@ -201,7 +201,46 @@ def known_answers(name):
     print(name, "ok")
 
 
+def fused_block_case(name, inp, oup, stride, channels, kernel_sizes, expand, active_fn, se_ratio, hw, batch, seed):
+    """One InvertedResidualChannelsFused (+ SqueezeAndExcitation) block of the reference in train mode:
+    forward, input gradient, every parameter gradient and the BN buffers after the step
+    (models/mobilenet_base.py:93-117,145-268; the block of the AtomNAS-C+ searched nets)."""
+    torch.manual_seed(seed)
+    bn_kw = {"momentum": 0.01, "eps": 1e-3}
+    blk = mb.InvertedResidualChannelsFused(inp, oup, stride, channels, kernel_sizes, expand,
+                                           active_fn=mb.get_active_fn(active_fn), batch_norm_kwargs=bn_kw,
+                                           se_ratio=se_ratio)
+    blk.apply(mb.init_weights_mnas)
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        for m in blk.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.weight.copy_(1.0 + 0.2 * torch.randn(m.weight.shape, generator=g))
+                m.bias.copy_(0.1 * torch.randn(m.bias.shape, generator=g))
+        if se_ratio is not None:                      # init_weights_mnas zeroes conv biases: make them matter
+            blk.se_op.se_reduce.bias.copy_(0.1 * torch.randn(blk.se_op.se_reduce.bias.shape, generator=g))
+            blk.se_op.se_expand.bias.copy_(0.1 * torch.randn(blk.se_op.se_expand.bias.shape, generator=g))
+    blk.train()
+    state0 = clone_sd(blk.state_dict())
+    x = torch.randn(batch, inp, hw, hw, generator=g, requires_grad=True)
+    y = blk(x)
+    wgt = torch.randn(y.shape, generator=g)
+    (y * wgt).sum().backward()
+    out = {"args": dict(inp=inp, oup=oup, stride=stride, channels=channels, kernel_sizes=kernel_sizes,
+                        expand=expand, active_fn=active_fn, se_ratio=se_ratio, bn_momentum=0.01, bn_eps=1e-3),
+           "state0": state0, "x": x.detach().clone(), "w": wgt, "y": y.detach().clone(),
+           "dx": x.grad.detach().clone(),
+           "grads": collections.OrderedDict((n, p.grad.detach().clone()) for n, p in blk.named_parameters()),
+           "state_after": clone_sd(blk.state_dict())}
+    torch.save(out, os.path.join(HERE, name + ".pt"))
+    print(name, "ok", tuple(y.shape))
+
+
 if __name__ == "__main__":
+    if os.environ.get("GOLDEN_ONLY") == "fused":           # only the fused / SE block fixtures
+        fused_block_case("tiny_fused_se_swish", 16, 16, 1, [16, 24, 8], [3, 5, 7], True, "nn.Swish", 0.5, 12, 3, 21)
+        fused_block_case("tiny_fused_relu_s2", 16, 24, 2, [24, 40], [3, 5], True, "nn.ReLU", None, 12, 3, 22)
+        sys.exit(0)
     train_case("tiny_supernet_train", TINY, 64, 4, 2, 3, 1e-4)
     for fn in ("nn.ReLU6", "nn.Swish"):
         kw = copy.deepcopy(TINY)

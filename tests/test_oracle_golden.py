@@ -160,3 +160,30 @@ def test_full_size_macs():
     assert pcf[i] == 304192 and pen[i] == pytest.approx(6.457615, rel=1e-6)
     j = names.index("features.22.ops.2.1.1.weight")
     assert pcf[j] == 27489 and pen[j] == pytest.approx(0.583557, rel=1e-6)
+
+
+@pytest.mark.parametrize("name", ["tiny_fused_se_swish", "tiny_fused_relu_s2"])
+def test_fused_se_block_matches_reference(name):
+    """Oracle restatement of InvertedResidualChannelsFused + SqueezeAndExcitation (scope table 8f-1,
+    the AtomNAS-C+ block) against the reference's own module: output, input gradient, every
+    parameter gradient, BN buffers after the step."""
+    import types
+    g = torch.load(os.path.join(G, name + ".pt"), weights_only=False)
+    a = g["args"]
+    spec = types.SimpleNamespace(bn_momentum=a["bn_momentum"], bn_eps=a["bn_eps"], active_fn=a["active_fn"])
+    st = {"blk." + k: v.clone() for k, v in g["state0"].items()}
+    params = [k for k, v in st.items() if v.dtype.is_floating_point and "running" not in k]
+    for k in params:
+        st[k].requires_grad_(True)
+    x = g["x"].clone().requires_grad_(True)
+    y = O.fused_block_forward(spec, st, "blk", x, a["inp"], a["oup"], a["stride"], a["channels"],
+                              a["kernel_sizes"], a["expand"], a["se_ratio"], training=True)
+    torch.testing.assert_close(y, g["y"], rtol=1e-5, atol=1e-5)
+    (y * g["w"]).sum().backward()
+    torch.testing.assert_close(x.grad, g["dx"], rtol=1e-4, atol=1e-5)
+    assert set("blk." + n for n in g["grads"]) == set(params)
+    for n, ref in g["grads"].items():
+        torch.testing.assert_close(st["blk." + n].grad, ref, rtol=1e-4, atol=1e-5, msg=n)
+    for k, v in g["state_after"].items():
+        if "running" in k or "num_batches" in k:
+            torch.testing.assert_close(st["blk." + k].detach(), v, rtol=1e-5, atol=1e-6, msg=k)
