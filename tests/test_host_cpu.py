@@ -259,3 +259,25 @@ def test_dropin_shims_build_the_yaml_model_like_the_reference():
     for k in ("rmsprop", "ema", "prune", "dist"):
         assert ours[k].startswith("atomnas_b200."), (k, ours[k])
     assert ours["config"].startswith(ref)
+
+
+@pytest.mark.parametrize("name", ["tiny_fused_se_swish", "tiny_fused_relu_s2"])
+def test_fused_block_surface_matches_reference_state_dict(name):
+    """The AtomNAS-C+ block's module surface (scope row 8f-1): same state_dict keys / shapes as the
+    reference's InvertedResidualChannelsFused (+SE), loads its weights, and refuses to run until its
+    kernels exist (no silent PyTorch fallback)."""
+    from atomnas_b200 import fused_block as fb
+    g = torch.load(os.path.join(G, name + ".pt"), weights_only=False)
+    a = g["args"]
+    blk = fb.InvertedResidualChannelsFused(a["inp"], a["oup"], a["stride"], a["channels"], a["kernel_sizes"],
+                                           a["expand"], active_fn=mb.get_active_fn(a["active_fn"]),
+                                           batch_norm_kwargs={"momentum": a["bn_momentum"], "eps": a["bn_eps"]},
+                                           se_ratio=a["se_ratio"])
+    sd = blk.state_dict()
+    assert list(sd.keys()) == list(g["state0"].keys())
+    for k, v in g["state0"].items():
+        assert tuple(sd[k].shape) == tuple(v.shape), k
+    assert blk.load_state_dict(g["state0"]).missing_keys == []
+    assert list(blk.get_named_depthwise_bn("p").keys()) == ["p.depth_ops.%d.1.1" % i for i in range(len(a["channels"]))]
+    with pytest.raises(NotImplementedError):
+        blk(g["x"])
