@@ -236,7 +236,38 @@ def fused_block_case(name, inp, oup, stride, channels, kernel_sizes, expand, act
     print(name, "ok", tuple(y.shape))
 
 
+def calibration_case(name, kwargs, input_size, batch, nbatches, seed):
+    """BN re-calibration as train.py:419-458 runs it: model.eval(); model.apply(bn_calibration)
+    (utils/common.py:213-226: reset stats, BN modules back to train(), momentum=None -> cumulative
+    average), a few no-grad forward passes, then eval-mode logits with the calibrated statistics."""
+    from utils.common import bn_calibration
+    model = build(kwargs, input_size, seed)
+    g = torch.Generator().manual_seed(seed + 3)
+    with torch.no_grad():                               # start from non-trivial running statistics
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.copy_(0.3 * torch.randn(m.running_mean.shape, generator=g))
+                m.running_var.copy_(0.5 + torch.rand(m.running_var.shape, generator=g))
+    state0 = clone_sd(model.state_dict())
+    model.eval()
+    model.apply(bn_calibration)
+    xs = [torch.randn(batch, 3, input_size, input_size, generator=g) for _ in range(nbatches)]
+    with torch.no_grad():
+        for x in xs:
+            model(x)
+    state_cal = clone_sd(model.state_dict())
+    model.eval()
+    with torch.no_grad():
+        logits = model(xs[0])
+    torch.save({"kwargs": kwargs, "input_size": input_size, "state0": state0, "xs": xs,
+                "state_calibrated": state_cal, "logits_eval": logits}, os.path.join(HERE, name + ".pt"))
+    print(name, "ok")
+
+
 if __name__ == "__main__":
+    if os.environ.get("GOLDEN_ONLY") == "calibration":
+        calibration_case("tiny_bn_calibration", TINY, 64, 4, 3, 31)
+        sys.exit(0)
     if os.environ.get("GOLDEN_ONLY") == "fused":           # only the fused / SE block fixtures
         fused_block_case("tiny_fused_se_swish", 16, 16, 1, [16, 24, 8], [3, 5, 7], True, "nn.Swish", 0.5, 12, 3, 21)
         fused_block_case("tiny_fused_relu_s2", 16, 24, 2, [24, 40], [3, 5], True, "nn.ReLU", None, 12, 3, 22)

@@ -187,3 +187,30 @@ def test_fused_se_block_matches_reference(name):
     for k, v in g["state_after"].items():
         if "running" in k or "num_batches" in k:
             torch.testing.assert_close(st["blk." + k].detach(), v, rtol=1e-5, atol=1e-6, msg=k)
+
+
+def test_bn_calibration_matches_reference():
+    """BN re-calibration (train.py:419-458 -> utils/common.py:213-226): running statistics reset,
+    momentum=None (cumulative average) over a few forward passes, then eval logits."""
+    g = torch.load(os.path.join(G, "tiny_bn_calibration.pt"), weights_only=False)
+    spec = O.NetSpec(**g["kwargs"], input_size=g["input_size"])
+    st = {k: v.clone() for k, v in g["state0"].items()}
+    for k in st:                                        # nn.BatchNorm2d.reset_running_stats()
+        if k.endswith("running_mean"):
+            st[k].zero_()
+        elif k.endswith("running_var"):
+            st[k].fill_(1.0)
+        elif k.endswith("num_batches_tracked"):
+            st[k].zero_()
+    spec.bn_momentum = None
+    with torch.no_grad():
+        for x in g["xs"]:
+            O.forward(spec, st, x, training=True)
+    for k, v in g["state_calibrated"].items():
+        if "running" in k:
+            torch.testing.assert_close(st[k], v, rtol=1e-4, atol=1e-5, msg=k)
+        elif "num_batches" in k:
+            assert int(st[k]) == int(v) == len(g["xs"])
+    with torch.no_grad():
+        logits = O.forward(spec, st, g["xs"][0], training=False)
+    torch.testing.assert_close(logits, g["logits_eval"], rtol=1e-4, atol=1e-4)
