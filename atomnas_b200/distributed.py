@@ -104,7 +104,8 @@ def _allreduce(tensors, coalesce=True, bucket_size_mb=-1):
     by_storage = {}
     for t in tensors:
         by_storage.setdefault((t.untyped_storage().data_ptr(), t.dtype), []).append(t)
-    for (_, _), group in by_storage.items():
+    loose = {}                                   # tensors with private storage, coalesced per dtype
+    for (_, dtype), group in by_storage.items():
         if len(group) > 1 and all(t.is_contiguous() for t in group):
             base = min(t.data_ptr() for t in group)
             end = max(t.data_ptr() + t.numel() * t.element_size() for t in group)
@@ -113,12 +114,14 @@ def _allreduce(tensors, coalesce=True, bucket_size_mb=-1):
             flat = first.as_strided((n,), (1,), first.storage_offset())
             _mean_allreduce_flat(flat, world)            # the arena range itself: no copies
         else:
-            flat = torch.cat([t.reshape(-1) for t in group])
-            _mean_allreduce_flat(flat, world)
-            off = 0
-            for t in group:
-                t.copy_(flat[off:off + t.numel()].view_as(t))
-                off += t.numel()
+            loose.setdefault(dtype, []).extend(group)
+    for dtype, group in loose.items():           # ONE flat buffer per dtype (utils/distributed.py:131-139)
+        flat = torch.cat([t.reshape(-1) for t in group])
+        _mean_allreduce_flat(flat, world)
+        off = 0
+        for t in group:
+            t.copy_(flat[off:off + t.numel()].view_as(t))
+            off += t.numel()
 
 
 def allreduce_grads(model, *args, **kwargs):

@@ -77,6 +77,7 @@ class Engine(object):
         self.dev = p0.device
         self.bufs = {}
         self.opt = None
+        self._fwd_gen = 0           # bumped by every forward; autograd nodes check it in backward
         self._build(root)
 
     # ------------------------------------------------------------------------------------------
@@ -289,6 +290,26 @@ class Engine(object):
             off, n = by_id[id(named_params[name])]
             self.l1_pen[off:off + n] = float(pen)
 
+    def set_weight_decay_method(self, method):
+        """Which elements take L2 (utils/optim.py:210-249).  'mnas': every conv / fc weight and the
+        classifier bias; 'slimmable': conv weights except depthwise ([N,1,k,k]) and fc weights, no
+        bias.  BN gamma / beta never; pad elements stay frozen (-1)."""
+        if method not in ("mnas", "slimmable"):
+            raise ValueError("Unknown weight_decay method: {}".format(method))
+        if getattr(self, "wd_method", "mnas") == method:
+            self.wd_method = method
+            return
+        self.wd_method = method
+        with torch.no_grad():
+            for prm, off, numel, wd, _ in self.param_slots:
+                if wd == 0.0:
+                    continue
+                flag = 1.0
+                if method == "slimmable":
+                    ps = list(prm.shape)
+                    flag = 1.0 if ((len(ps) == 4 and ps[1] != 1) or len(ps) == 2) else 0.0
+                self.wd_flag[off:off + numel] = flag
+
     def refresh_weights(self, force=False):
         """Re-materialise bf16 / transposed / tap-major weight copies from the fp32 masters."""
         ver = sum(p._version for p, _, _, _, _ in self.param_slots if p.dim() > 1)
@@ -381,6 +402,8 @@ class Engine(object):
         bf.part = torch.empty(part_max, device=dev)
         if need_grad:
             bf.wpart = torch.empty(wpart_max, device=dev)
+            pad_w = [br.hp * br.k * br.k for p in self.blocks for br in p.branches if br.hp != br.h]
+            bf.dw_tmp = torch.empty(max(pad_w), device=dev) if pad_w else None
             bf.g_d = bf16(big_d)
             bf.g_e = bf16(big_e)
             bf.dp = bf16(big_y)
@@ -416,15 +439,24 @@ class Engine(object):
 
     def _begin_bn_step(self, training):
         """Per-forward BN bookkeeping: num_batches_tracked and the momentum to use
-        (momentum=None => cumulative average, utils/common.py:214-226)."""
+        (momentum=None => cumulative average, utils/common.py:214-226).  Cumulative mode needs the
+        counters on the host: ONE device->host read of the counter arena per forward (calibration
+        runs 10-16 forwards), never one per BN."""
         if training:
             self.NBT.add_(1)              # every num_batches_tracked buffer is a view of this arena
+        counts, i = None, 0
         for g in self.bn_groups:
             bn = g.members[0][0]
             if training and bn.track_running_stats:
-                g.mom_now = (1.0 / float(bn.num_batches_tracked.item())) if bn.momentum is None else bn.momentum
+                if bn.momentum is None:
+                    if counts is None:
+                        counts = self.NBT.tolist()
+                    g.mom_now = 1.0 / float(max(1, counts[i]))
+                else:
+                    g.mom_now = bn.momentum
             else:
                 g.mom_now = 0.0
+            i += len(g.members)
 
     # ------------------------------------------------------------------------------------------
     # forward
@@ -438,6 +470,7 @@ class Engine(object):
         else:
             B, H, W, _ = x.shape
         bf = self._buffers(B, H, W, need_grad)
+        self._fwd_gen += 1
         bf.training, bf.seed, bf.seed_dev = training, seed, seed_dev
         self._begin_bn_step(training)
         part = bf.part
@@ -653,7 +686,7 @@ class Engine(object):
         """Depthwise weight gradient of a branch whose width is not a multiple of 8: run on the
         padded slot into scratch, then keep the first h rows (pad rows are exactly zero)."""
         o = br.off
-        tmp = torch.empty(br.hp * br.k * br.k, device=self.dev)
+        tmp = next(iter(self.bufs.values())).dw_tmp          # sized at plan time (graph safe)
         K.dw_bwd_weight(g_d[o:], bb.d_raw[:, o:], usrc[:, o:], None, None, None, None, None, 0, wpart, tmp, B,
                         bb.hin, bb.win, br.hp, br.k, p.stride, ldg=p.Kh, ldd=p.Kh, lde=ld_src)
         n = br.h * br.k * br.k
@@ -748,6 +781,16 @@ def invalidate(module):
             del _ENGINES[root]
 
 
+def _check_generation(ctx):
+    """The engine keeps ONE set of saved activations: a second forward (another batch shape, an eval
+    pass, gradient accumulation with two live graphs) overwrites them.  Refuse to compute gradients
+    from the wrong activations instead of doing it silently."""
+    if ctx.eng._fwd_gen != ctx.gen:
+        raise RuntimeError("atomnas_b200: backward() of a forward whose saved activations were overwritten by a "
+                           "later forward of the same module (the engine keeps one activation set); run "
+                           "forward -> backward pairs back to back")
+
+
 class _NetFunction(torch.autograd.Function):
     """The whole network as ONE autograd node: forward runs the kernel sequence, backward fills
     the gradient arena and hands PyTorch views of it."""
@@ -756,11 +799,13 @@ class _NetFunction(torch.autograd.Function):
     def forward(ctx, eng, x, seed, *params):
         ctx.eng = eng
         out = eng.forward(x, True, True, seed)
+        ctx.gen = eng._fwd_gen
         return out.clone()
 
     @staticmethod
     def backward(ctx, dlogits):
         eng = ctx.eng
+        _check_generation(ctx)
         eng.set_dlogits(dlogits)
         eng.backward(None)
         return (None, None, None) + tuple(eng.param_grad_views())
@@ -771,11 +816,14 @@ class _BlockFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, eng, x_nhwc, *params):
         ctx.eng = eng
-        return eng.forward(x_nhwc, True, True).clone()
+        out = eng.forward(x_nhwc, True, True).clone()
+        ctx.gen = eng._fwd_gen
+        return out
 
     @staticmethod
     def backward(ctx, dy):
         eng = ctx.eng
+        _check_generation(ctx)
         dx = eng.backward(dy.contiguous())
         return (None, dx.clone()) + tuple(eng.param_grad_views())
 

@@ -31,6 +31,13 @@ class _Flat(object):
             slots = {id(p): (off, n) for p, off, n, _, _ in eng.param_slots}
             self.slots = [slots[id(p)] for p in params]
             self.wd_flag, self.l1_pen = eng.wd_flag, eng.l1_pen
+            if set(id(p) for p in params) != set(slots.keys()):
+                # this param_group covers only part of the engine's arena (several groups, frozen
+                # parameters, params without gradients): every element outside it is frozen (-1) for
+                # this launch, as the reference's per-parameter loop would skip it (rmsprop.py:81-85)
+                self.wd_flag = torch.full_like(eng.wd_flag, -1.0)
+                for o, k in self.slots:
+                    self.wd_flag[o:o + k] = eng.wd_flag[o:o + k]
         else:
             dev = params[0].device
             offs, n = [], 0

@@ -1,13 +1,18 @@
 #!/usr/bin/env python
-"""Benchmark of the hot path: AtomNAS-C supernet training step on B200.
+"""Benchmark of the hot path: AtomNAS supernet training step on B200.
 
-    python bench.py --gpus N --steps K --warmup W            # this repo (sm_100a kernels)
-    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on host cores
+    python bench.py --gpus N --steps K --warmup W              # this repo (sm_100a kernels)
+    python bench.py --impl reference --gpus N --steps K ...    # the unmodified reference on the host cores
+    python bench.py --impl reference-gpu [--ref-mode fp32|bf16]  # the unmodified reference modules on the same B200
+    python bench.py --model atomnas_a                          # BASELINE config 2 (AtomNAS-A supernet)
+    python bench.py --masks random|searched                    # BASELINE config 3 fixtures (ii)/(iii): shrink first
+    python bench.py --accum 8                                  # (S) series: 8 micro-batches of 256 per optimizer step
 
 One "step" = forward + label-smoothed CE + backward + gradient all-reduce + RMSprop (with the
 analytic L2 / BN-gamma L1 terms) + EMA, on one synthetic ImageNet-shaped batch of 256 images per
 GPU (weak scaling: global batch 256*N, 2048 at N=8 -- BASELINE.json configs[2]).  Prints ONE JSON
-line (contract in the task statement / DESIGN.md "Measurement").
+line (contract in the task statement / DESIGN.md "Measurement").  Under torchrun every rank runs
+every collective of every phase; rank 0 prints.
 """
 import argparse
 import json
@@ -23,17 +28,31 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+_SETTING = [[6, 24, 4, 2, [3, 5, 7]], [6, 40, 4, 2, [3, 5, 7]], [6, 80, 4, 2, [3, 5, 7]], [6, 96, 4, 1, [3, 5, 7]],
+            [6, 192, 4, 2, [3, 5, 7]], [6, 320, 1, 1, [3, 5, 7]]]
 ATOMNAS_C_SUPERNET = dict(      # apps/slimming/shrink/atomnas_c.yml -> supernet_single_path_nas_relu.yml
     num_classes=1000, input_channel=32, last_channel=1280, width_mult=1.0, round_nearest=8,
-    inverted_residual_setting=[[1, 16, 1, 1, [3]], [6, 24, 4, 2, [3, 5, 7]], [6, 40, 4, 2, [3, 5, 7]],
-                               [6, 80, 4, 2, [3, 5, 7]], [6, 96, 4, 1, [3, 5, 7]],
-                               [6, 192, 4, 2, [3, 5, 7]], [6, 320, 1, 1, [3, 5, 7]]],
+    inverted_residual_setting=[[1, 16, 1, 1, [3]]] + _SETTING,
     dropout_ratio=0.2, batch_norm_momentum=0.01, batch_norm_epsilon=1e-3, active_fn="nn.ReLU",
     block="InvertedResidualChannels")
+ATOMNAS_A_SUPERNET = dict(      # apps/slimming/shrink/atomnas_a.yml -> supernet_single_path_nas_relu_small.yml
+    ATOMNAS_C_SUPERNET, input_channel=16)
+MODELS = {"atomnas_c": ("AtomNAS-C supernet (apps/slimming/shrink/atomnas_c.yml)", ATOMNAS_C_SUPERNET),
+          "atomnas_a": ("AtomNAS-A supernet (apps/slimming/shrink/atomnas_a.yml)", ATOMNAS_A_SUPERNET)}
+# apps/searched/models/atomnas_c.yml:14-35 -- per-branch widths of the searched AtomNAS-C (the end
+# state of the shrink): (kernel sizes, hidden widths) per block; mask fixture (iii) keeps the first n atoms.
+SEARCHED_C = [[[3], [32]], [[3, 5, 7], [15, 23, 13]], [[3, 5, 7], [20, 3, 2]], [[3, 5, 7], [21, 8, 1]],
+              [[3, 5], [21, 4]], [[3, 5, 7], [64, 65, 70]], [[3, 5, 7], [40, 23, 28]], [[3, 5, 7], [36, 21, 9]],
+              [[3, 5, 7], [40, 22, 7]], [[3, 5, 7], [169, 170, 157]], [[3, 5, 7], [45, 55, 74]],
+              [[3, 5, 7], [58, 21, 37]], [[3, 5, 7], [77, 18, 39]], [[3, 5, 7], [393, 263, 247]],
+              [[3, 5, 7], [57, 40, 36]], [[3, 5, 7], [61, 34, 26]], [[3, 5, 7], [87, 38, 33]],
+              [[3, 5, 7], [454, 468, 468]], [[3, 5, 7], [188, 137, 306]], [[3, 5, 7], [253, 187, 314]],
+              [[3, 5, 7], [345, 202, 233]], [[3, 5, 7], [823, 738, 749]]]
 PER_GPU_BATCH = 256
 IMAGE = 224
 RHO = 1.0e-4            # post-warm-up L1 weight (atomnas_c.yml prune_params.rho): pruning term active
 WEIGHT_DECAY = 1.0e-5
+METRIC = "images/sec AtomNAS-C supernet fwd+bwd+RMSprop bf16"
 
 
 def load_peaks():
@@ -83,11 +102,11 @@ class ClockSampler(object):
                 "reasons": reasons, "samples": len(sm)}
 
 
-def build_model():
+def build_model(kwargs=ATOMNAS_C_SUPERNET):
     from atomnas_b200 import mobilenet_base as mb
     from atomnas_b200 import mobilenet_supernet as ms
     torch.manual_seed(1995)
-    model = ms.MobileNetV2(**ATOMNAS_C_SUPERNET, input_size=IMAGE)
+    model = ms.MobileNetV2(**kwargs, input_size=IMAGE)
     model.apply(mb.init_weights_mnas)
     return model
 
@@ -98,9 +117,32 @@ def build_trainer(model, world, use_graph):
     prune.profile_macs(model, IMAGE)
     info = prune.get_bn_to_prune(model, {"bn_prune_filter": "expansion_only_skip_expand1"}, verbose=False)
     gb = PER_GPU_BATCH * world
-    return Trainer(model, lr=0.016 * gb / 256, alpha=0.9, momentum=0.9, eps=1e-3, eps_inside_sqrt=True,
-                   weight_decay=WEIGHT_DECAY, label_smoothing=0.1, ema_decay=0.9999 ** (gb / 4096.0),
-                   prune_penalties=list(zip(info.weight, info.penalty)), use_cuda_graph=use_graph)
+    tr = Trainer(model, lr=0.016 * gb / 256, alpha=0.9, momentum=0.9, eps=1e-3, eps_inside_sqrt=True,
+                 weight_decay=WEIGHT_DECAY, label_smoothing=0.1, ema_decay=0.9999 ** (gb / 4096.0),
+                 prune_penalties=list(zip(info.weight, info.penalty)), use_cuda_graph=use_graph)
+    return tr, info
+
+
+def mask_fixture(model, kind):
+    """BASELINE config 3 mask fixtures: 'random' = keep-probability 0.5 per atom with
+    manual_seed(1995); 'searched' = first n atoms of every branch alive, n from
+    apps/searched/models/atomnas_c.yml:14-35 (1521 M -> 360 M MACs)."""
+    g = torch.Generator().manual_seed(1995)
+    masks = {}
+    for i, (name, block) in enumerate(model.get_named_block_list().items()):
+        ms_ = []
+        for j, (k, c) in enumerate(zip(block.kernel_sizes, block.channels)):
+            if kind == "random":
+                m = torch.rand(c, generator=g) < 0.5
+                if not block.expand:
+                    m[:] = True
+            else:
+                ks, hid = SEARCHED_C[i]
+                n = hid[ks.index(k)] if k in ks else 0
+                m = torch.arange(c) < n
+            ms_.append(m.cuda())
+        masks[name] = ms_
+    return masks
 
 
 def timed_loop(fn, steps, world):
@@ -122,40 +164,40 @@ def timed_loop(fn, steps, world):
 
 
 # ------------------------------------------------------------------------------------------------
-# algorithmic work per kernel family (DESIGN.md "Measurement": each tensor counted once per pass)
+# algorithmic work per kernel class, SURVEY 8(d) convention: every tensor a pass touches counted
+# ONCE per pass (forward, data gradient, weight gradient); re-reads of saved tensors by fused
+# epilogues / prologues are NOT billed.
 # ------------------------------------------------------------------------------------------------
+CLASSES = {"an_dw_fwd": "depthwise", "an_dw_bwd_data": "depthwise", "an_dw_bwd_weight": "depthwise",
+           "an_dw_bwd": "depthwise",
+           "an_pw_gemm": "pointwise", "an_pw_wgrad": "pointwise", "an_wgrad_reduce": "pointwise",
+           "an_affine_act": "elementwise", "an_col_reduce": "elementwise", "an_act_bwd_reduce": "elementwise",
+           "an_bn_finalize": "bn_finalize", "an_bn_bwd_finalize": "bn_finalize"}
+
+
 def algorithmic_work(eng, B):
-    """{(entry point, tag): (bytes, flops)} per step for the conv kernels of the 22 blocks."""
-    work = {}
-
-    def add(key, nbytes, flops):
-        b, f = work.get(key, (0, 0))
-        work[key] = (b + nbytes, f + flops)
-
+    """{class: (bytes, flops)} per training step for the 22 blocks + head."""
+    work = {"depthwise": [0, 0], "pointwise": [0, 0]}
     h = IMAGE // 2
     for p in eng.blocks:
         ho = h // 2 if p.stride == 2 else h
         M, Mo = B * h * h, B * ho * ho
+        if not p.branches:
+            h = ho
+            continue
         if p.expand:
-            fl = 2 * M * p.Kh * p.inp
-            add(("an_pw_gemm", "fwd.expand"), 2 * (M * p.inp + M * p.Kh), fl)
-            add(("an_affine_act", "fwd.expand"), 2 * (2 * M * p.Kh), 0)          # u = act(bn(e_raw))
-            add(("an_pw_wgrad", "bwd.expand_wgrad"), 2 * (2 * M * p.Kh + M * p.inp), fl)
-            add(("an_pw_gemm", "bwd.expand_dgrad"), 2 * (2 * M * p.Kh + M * p.inp * (2 if p.res else 1)), fl)
+            work["pointwise"][0] += 3 * 2 * M * (p.inp + p.Kh)
+            work["pointwise"][1] += 3 * 2 * M * p.Kh * p.inp
         for br in p.branches:
-            fl = 2 * Mo * br.hp * br.k * br.k
-            add(("an_dw_fwd", "fwd.dw%d" % br.k), 2 * (M * br.hp + Mo * br.hp), fl)
-            # dd in, activation-derivative operand (e_raw) in, g_e out
-            add(("an_dw_bwd_data", "bwd.dw%d_dgrad" % br.k), 2 * (Mo * br.hp + 2 * M * br.hp), fl)
-            add(("an_dw_bwd_weight", "bwd.dw%d_wgrad" % br.k), 2 * (Mo * br.hp + M * br.hp), fl)
-        add(("an_affine_act", "bwd.dd"), 2 * (3 * Mo * p.Kh), 0)                  # dd = ca*g + cb*d_raw + cc
-        add(("an_affine_act", "fwd.project"), 2 * (Mo * p.oup * (3 if p.res else 2)), 0)
-        add(("an_affine_act", "bwd.pw_bn"), 2 * (3 * Mo * p.oup), 0)
-        fl = 2 * Mo * p.Kh * p.oup
-        add(("an_pw_gemm", "fwd.project"), 2 * (Mo * p.Kh + Mo * p.oup), fl)
-        add(("an_pw_wgrad", "bwd.project_wgrad"), 2 * (Mo * p.Kh + Mo * p.oup), fl)
-        add(("an_pw_gemm", "bwd.project_dgrad"), 2 * (Mo * p.oup + 2 * Mo * p.Kh), fl)
+            work["depthwise"][0] += 3 * 2 * (M + Mo) * br.hp
+            work["depthwise"][1] += 3 * 2 * Mo * br.hp * br.k * br.k
+        work["pointwise"][0] += 3 * 2 * Mo * (p.Kh + p.oup)
+        work["pointwise"][1] += 3 * 2 * Mo * p.Kh * p.oup
         h = ho
+    hd = eng.head
+    Mh = B * h * h
+    work["pointwise"][0] += 3 * 2 * Mh * (hd.cin + hd.C)
+    work["pointwise"][1] += 3 * 2 * Mh * hd.cin * hd.C
     return work
 
 
@@ -167,64 +209,121 @@ def profile_kernels(trainer, x, y, peaks, steps=2):
     rec = L.stop_profile()
     total_ms = sum(v[1] for v in rec.values())
     work = algorithmic_work(trainer.eng, x.shape[0])
-    families = {}
+    families, classes = {}, {}
     for (name, tag), (calls, ms) in rec.items():
-        f = families.setdefault(name, {"ms": 0.0, "calls": 0, "bytes": 0, "flops": 0})
+        f = families.setdefault(name, {"ms": 0.0, "calls": 0})
         f["ms"] += ms / steps
         f["calls"] += calls // steps
-        if (name, tag) in work:
-            f["bytes"] += work[(name, tag)][0]
-            f["flops"] += work[(name, tag)][1]
-    table = []
-    for name, f in sorted(families.items(), key=lambda kv: -kv[1]["ms"]):
-        row = {"kernel": name, "ms_per_step": round(f["ms"], 3), "launches_per_step": f["calls"],
-               "share": round(f["ms"] * steps / total_ms, 4)}
-        if f["bytes"]:
-            row["algorithmic_GBps"] = round(f["bytes"] / (f["ms"] * 1e-3) / 1e9, 1)
+        c = classes.setdefault(CLASSES.get(name, "other"), {"ms": 0.0, "calls": 0})
+        c["ms"] += ms / steps
+        c["calls"] += calls // steps
+    table = [{"kernel": name, "class": CLASSES.get(name, "other"), "ms_per_step": round(f["ms"], 3),
+              "launches_per_step": f["calls"], "share": round(f["ms"] * steps / total_ms, 4)}
+             for name, f in sorted(families.items(), key=lambda kv: -kv[1]["ms"])]
+    ctable = []
+    for name, c in sorted(classes.items(), key=lambda kv: -kv[1]["ms"]):
+        row = {"class": name, "ms_per_step": round(c["ms"], 3), "launches_per_step": c["calls"],
+               "share": round(c["ms"] * steps / total_ms, 4)}
+        if name in work:
+            nbytes, flops = work[name]
+            row["algorithmic_GB"] = round(nbytes / 1e9, 3)
+            row["algorithmic_GBps"] = round(nbytes / (c["ms"] * 1e-3) / 1e9, 1)
             row["frac_hbm"] = round(row["algorithmic_GBps"] / peaks["hbm_gbs"], 4)
-            row["algorithmic_TFLOPs"] = round(f["flops"] / (f["ms"] * 1e-3) / 1e12, 2)
+            row["algorithmic_TFLOPs"] = round(flops / (c["ms"] * 1e-3) / 1e12, 2)
             row["frac_tensor_sustained"] = round(row["algorithmic_TFLOPs"] / peaks["bf16_tflops_sustained"], 4)
-        table.append(row)
+        ctable.append(row)
     by_tag = {"%s|%s" % k: round(v[1] / steps, 3) for k, v in sorted(rec.items(), key=lambda kv: -kv[1][1])[:24]}
-    return table, by_tag, total_ms / steps
+    return table, ctable, by_tag, total_ms / steps
+
+
+def measured_traffic(cls, model_key, batch):
+    """dram__bytes_read.sum + dram__bytes_write.sum per step of a kernel class, from the committed
+    ncu capture of this same command (profiles/r02_dram_by_class.json), or None."""
+    path = os.path.join(ROOT, "profiles", "r02_dram_by_class.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        d = json.load(f)
+    if d.get("model") != model_key or d.get("batch") != batch:
+        return None
+    return d.get("classes", {}).get(cls, {}).get("dram_bytes_per_step")
 
 
 # ------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle's train step on the host cores
+# reference arms: the UNMODIFIED reference (oracle/_ref, staged by oracle/make_ref.py) -- on the host
+# cores (the CPU arm / cpu_baseline) or on the same B200 (the cuDNN bar); the oracle port only when
+# oracle/_ref is absent
 # ------------------------------------------------------------------------------------------------
-def cpu_reference(steps, warmup, batch):
-    from oracle import atomnas_oracle as O
+def cpu_reference(kwargs, steps, warmup, batch, budget_s=200.0):
+    from oracle import ref_runner as RR
     cores = os.cpu_count() or 1
-    spec = O.NetSpec(**ATOMNAS_C_SUPERNET, input_size=IMAGE)
-    ts = O.TrainState(spec, O.init_state(spec, 1995))
     g = torch.Generator().manual_seed(0)
-    x = torch.randn(batch, 3, IMAGE, IMAGE, generator=g)
-    y = torch.randint(0, 1000, (batch,), generator=g)
+    kind = "reference" if RR.available() else "port"
+    if kind == "reference":
+        st = RR.train_state(kwargs, IMAGE, device="cpu", lr=0.016 * 8)
 
-    def one():
+        def run(x, y):
+            RR.train_step(st, x, y, WEIGHT_DECAY, RHO)
+    else:
+        from oracle import atomnas_oracle as O
+        spec = O.NetSpec(**kwargs, input_size=IMAGE)
+        ts = O.TrainState(spec, O.init_state(spec, 1995))
+
+        def run(x, y):
+            O.train_step(ts, x, y, 0.016 * 8, WEIGHT_DECAY, RHO, 0.1, 0.9999 ** 0.5)
+
+    def data(b):
+        return torch.randn(b, 3, IMAGE, IMAGE, generator=g), torch.randint(0, 1000, (b,), generator=g)
+
+    def one(x, y):
         t0 = time.perf_counter()
-        O.train_step(ts, x, y, 0.016 * 8, WEIGHT_DECAY, RHO, 0.1, 0.9999 ** 0.5)
+        run(x, y)
         return time.perf_counter() - t0
 
     # thread count: the oneDNN depthwise/1x1 primitives at this batch stop scaling well before a
-    # large host's core count, so take the fastest of {all, 1/2, 1/4, 1/8} cores (one step each)
+    # large host's core count, so take the fastest of {all, 1/2, 1/4, 1/8, 1/16} of the cores
+    x, y = data(batch)
     best_t, best_n = None, cores
-    for n in sorted({max(min(cores, 8), cores // d) for d in (16, 8, 4, 2, 1)}):
+    t_start = time.perf_counter()
+    for n in sorted({max(min(cores, 8), cores // d) for d in (1, 2, 4, 8, 16)}, reverse=True):
         torch.set_num_threads(n)
-        for _ in range(max(1, warmup)):            # primitive creation per shape happens here
-            one()
-        t = one()
+        one(x, y)                                      # primitive creation per shape happens here
+        t = one(x, y)
         if best_t is None or t < best_t:
             best_t, best_n = t, n
-        elif t > 1.2 * best_t:                      # past the knee (or a CPU quota): stop escalating
+        if time.perf_counter() - t_start > 0.4 * budget_s:
             break
     torch.set_num_threads(best_n)
-    one()
-    times = [one() for _ in range(steps)]
+    # bounded sample: shrink the per-step batch until warmup + steps fit the budget
+    while batch > 8 and (steps + warmup) * best_t * 1.1 > 0.6 * budget_s:
+        batch //= 2
+        x, y = data(batch)
+        one(x, y)
+        best_t = one(x, y)
+    for _ in range(warmup):
+        one(x, y)
+    times = [one(x, y) for _ in range(steps)]
     sec = sum(times) / len(times)
-    return {"value": batch / sec, "unit": "images/sec", "cores": best_n, "host_cores": cores, "kind": "port",
-            "sample": "%d timed steps of batch %d after warm-up (same network, loss, optimizer; fp32 torch CPU ops; "
-                      "thread count = fastest of cores/{8,4,2,1})" % (steps, batch)}, sec
+    what = ("unmodified reference modules (oracle/_ref: models.mobilenet_supernet, utils.rmsprop, utils.optim, "
+            "utils.prune), fp32 as shipped") if kind == "reference" else "oracle port (fp32 torch CPU ops)"
+    return {"value": batch / sec, "unit": "images/sec", "cores": best_n, "host_cores": cores, "kind": kind,
+            "sample": "%d timed steps of batch %d after %d warm-up steps; %s; train.py:174-236 loop body; "
+                      "thread count = fastest of cores/{1,2,4,8,16}" % (steps, batch, warmup, what)}, sec, batch
+
+
+def gpu_reference(kwargs, steps, warmup, mode):
+    """The reference's own nn.Modules / RMSprop / EMA loop on cuda:0 (cuDNN, ATen): 'fp32' = as
+    shipped (train.py:255 sets cudnn.benchmark; TF32 convs are torch's default), 'bf16' = its best
+    light (autocast bf16 + channels_last)."""
+    from oracle import ref_runner as RR
+    torch.backends.cudnn.benchmark = True
+    st = RR.train_state(kwargs, IMAGE, device="cuda", lr=0.016, channels_last=(mode == "bf16"))
+    gen = torch.Generator(device="cuda").manual_seed(1995)
+    x = torch.randn(PER_GPU_BATCH, 3, IMAGE, IMAGE, device="cuda", generator=gen)
+    y = torch.randint(0, 1000, (PER_GPU_BATCH,), device="cuda", generator=gen)
+    for _ in range(warmup):
+        RR.train_step(st, x, y, WEIGHT_DECAY, RHO, autocast_bf16=(mode == "bf16"))
+    return timed_loop(lambda: RR.train_step(st, x, y, WEIGHT_DECAY, RHO, autocast_bf16=(mode == "bf16")), steps, 1)
 
 
 def main():
@@ -232,7 +331,11 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference-gpu"])
+    ap.add_argument("--ref-mode", default="bf16", choices=["fp32", "bf16"])
+    ap.add_argument("--model", default="atomnas_c", choices=sorted(MODELS))
+    ap.add_argument("--masks", default="dense", choices=["dense", "random", "searched"])
+    ap.add_argument("--accum", type=int, default=1, help="micro-batches of 256 per optimizer step ((S) series)")
     ap.add_argument("--no-graph", action="store_true", help="do not replay the step from a CUDA graph")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -241,20 +344,25 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     warmup = max(3, args.warmup)
-    config = {"workload": "AtomNAS-C supernet (apps/slimming/shrink/atomnas_c.yml) training step, "
-                          "synthetic 3x224x224, %d images per GPU, dynamic BN-gamma pruning term active "
-                          "(rho=1e-4)" % PER_GPU_BATCH,
-              "global_batch": PER_GPU_BATCH * world, "per_gpu_batch": PER_GPU_BATCH, "image": IMAGE,
-              "parallelism": "dp%d" % world,
+    model_name, kwargs = MODELS[args.model]
+    masks_txt = {"dense": "dense (no shrink yet)", "random": "shrunk with the random keep-0.5 mask fixture",
+                 "searched": "shrunk to the searched AtomNAS-C widths (apps/searched/models/atomnas_c.yml)"}[args.masks]
+    config = {"workload": "%s training step, synthetic 3x224x224, %d images per GPU%s, dynamic BN-gamma pruning "
+                          "term active (rho=1e-4), %s" % (model_name, PER_GPU_BATCH,
+                                                         " x %d micro-batches" % args.accum if args.accum > 1 else "",
+                                                         masks_txt),
+              "global_batch": PER_GPU_BATCH * world * args.accum, "per_gpu_batch": PER_GPU_BATCH, "image": IMAGE,
+              "parallelism": "dp%d" % world, "model": args.model, "masks": args.masks, "accum": args.accum,
               "cache": "inputs larger than L2 (154 MB images + ~14 GB of saved activations per step)"}
 
     if args.impl == "reference":
         if rank != 0:
             return
-        base, sec = cpu_reference(min(args.steps, 4), 1, 32)
-        out = {"impl": "reference", "metric": "images/sec AtomNAS-C supernet fwd+bwd+RMSprop bf16",
-               "value": base["value"],
-               "unit": "images/sec", "n_gpus": args.gpus, "steps": min(args.steps, 4), "warmup": 1,
+        base, sec, batch = cpu_reference(kwargs, max(1, args.steps), max(0, args.warmup), 64)
+        config = dict(config, sample="reference arm: each step is a bounded sample of %d images of the %d-image "
+                                     "workload on the host cores" % (batch, PER_GPU_BATCH))
+        out = {"impl": "reference", "metric": METRIC, "value": base["value"],
+               "unit": "images/sec", "n_gpus": args.gpus, "steps": max(1, args.steps), "warmup": max(0, args.warmup),
                "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "f32", "data": "synthetic", "config": config, "cpu_baseline": base,
                "e2e": {"value": base["value"], "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -262,80 +370,128 @@ def main():
         return
 
     torch.cuda.set_device(local_rank)
+    if args.impl == "reference-gpu":
+        if rank != 0:
+            return
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        sec = gpu_reference(kwargs, args.steps, warmup, args.ref_mode)
+        clocks = sampler.stop()
+        out = {"impl": "reference-gpu", "ref_mode": args.ref_mode, "metric": METRIC,
+               "value": PER_GPU_BATCH * args.steps / sec, "unit": "images/sec", "n_gpus": 1, "steps": args.steps,
+               "warmup": warmup, "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "f32 (TF32 convs)" if args.ref_mode == "fp32" else "bf16 autocast",
+               "data": "synthetic", "config": config, "clocks": clocks,
+               "note": "unmodified reference nn.Modules + utils.rmsprop + EMA loop (oracle/_ref) on cuda:0 through "
+                       "PyTorch eager / cuDNN; %s" % ("as shipped (fp32 NCHW, cudnn.benchmark)" if args.ref_mode == "fp32"
+                                                      else "autocast bf16 + channels_last + cudnn.benchmark"),
+               "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 1e9, 2)}
+        print(json.dumps(out))
+        return
+
     if world > 1:
         dist.init_process_group("nccl")
     from atomnas_b200 import _lib as L
     peaks = load_peaks()
-    model = build_model().cuda()
+    model = build_model(kwargs).cuda()
     if world > 1:                                     # replicas start identical (utils/distributed.py:183-190)
         for t in list(model.parameters()) + list(model.buffers()):
             dist.broadcast(t.data, 0)
     model.train()
-    trainer = build_trainer(model, world, use_graph=not args.no_graph)
+    trainer, info = build_trainer(model, world, use_graph=not args.no_graph)
+    shrink_info = None
+    if args.masks != "dense":
+        shrink_info = trainer.shrink(masks=mask_fixture(model, args.masks), prune_info=info)
+        from atomnas_b200 import prune
+        shrink_info["macs_after"] = int(prune.profile_macs(model, IMAGE))
     gen = torch.Generator(device="cuda").manual_seed(1995 + rank)
     x = torch.randn(PER_GPU_BATCH, 3, IMAGE, IMAGE, device="cuda", generator=gen)
     y = torch.randint(0, 1000, (PER_GPU_BATCH,), device="cuda", generator=gen)
     x_host = x.cpu().pin_memory()
     y_host = y.cpu().pin_memory()
 
+    if args.accum > 1:
+        def one_step():
+            return trainer.step_accum([(x, y)] * args.accum, rho=RHO)
+    else:
+        def one_step():
+            return trainer.step(x, y, rho=RHO)
+
     for _ in range(warmup):
-        trainer.step(x, y, rho=RHO)
+        one_step()
     torch.cuda.synchronize()
     launches0 = L.lib().an_launch_count()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    sec = timed_loop(lambda: trainer.step(x, y, rho=RHO), args.steps, world)
+    sec = timed_loop(one_step, args.steps, world)
     clocks = sampler.stop() if rank == 0 else None
     launches = L.lib().an_launch_count() - launches0
     per_step_launches = trainer.launches_per_step if getattr(trainer, "launches_per_step", None) else launches // args.steps
+    per_step_launches *= args.accum if trainer.launches_per_step and args.accum > 1 else 1
 
     # end to end through the public API: pinned host -> device copies and a loss read every step
     last = [None]
 
     def e2e_step():
         # the next batch's H2D copy runs on a side stream under this step (DataPrefetcher pattern)
-        last[0] = trainer.step_host(x_host, y_host, rho=RHO, prefetch=(x_host, y_host)).item()
+        if args.accum > 1:
+            last[0] = trainer.step_accum_host([(x_host, y_host)] * args.accum, rho=RHO).item()
+        else:
+            last[0] = trainer.step_host(x_host, y_host, rho=RHO, prefetch=(x_host, y_host)).item()
 
     for _ in range(2):
         e2e_step()
     sec_e2e = timed_loop(e2e_step, args.steps, world)
     loss_value = last[0]
 
+    # per-kernel pass: eager launches bracketed by CUDA events.  EVERY rank runs it (the step holds
+    # collectives); only rank 0 reports.
+    prof = None
+    if not args.no_profile and args.accum == 1:
+        was = trainer.use_cuda_graph
+        trainer.use_cuda_graph = False               # per-kernel CUDA events need real launches
+        prof = profile_kernels(trainer, x, y, peaks)
+        trainer.use_cuda_graph = was
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
-    imgs = PER_GPU_BATCH * world
-    out = {"metric": "images/sec AtomNAS-C supernet fwd+bwd+RMSprop bf16", "value": imgs * args.steps / sec,
+
+    imgs = PER_GPU_BATCH * world * args.accum
+    out = {"metric": METRIC, "value": imgs * args.steps / sec,
            "unit": "images/sec", "n_gpus": world, "steps": args.steps, "warmup": warmup,
            "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "bf16", "data": "synthetic", "config": config, "clocks": clocks,
            "e2e": {"value": imgs * args.steps / sec_e2e, "unit": "images/sec",
-                   "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 8, "d2h_bytes_per_step": 4,
+                   "h2d_bytes_per_step": (x_host.numel() * 4 + y_host.numel() * 8) * args.accum, "d2h_bytes_per_step": 4,
                    "ms_per_step": sec_e2e / args.steps * 1e3},
            "gpu_launches": int(per_step_launches * args.steps), "gpu_launches_per_step": int(per_step_launches),
            "cuda_graph": bool(trainer.use_cuda_graph), "final_loss": loss_value, "peaks": peaks}
-    if not args.no_profile:
-        trainer_p = trainer
-        was = trainer_p.use_cuda_graph
-        trainer_p.use_cuda_graph = False            # per-kernel CUDA events need real launches
-        table, by_tag, prof_ms = profile_kernels(trainer_p, x, y, peaks)
-        trainer_p.use_cuda_graph = was
-        top = next((r for r in table if "algorithmic_GBps" in r), None)
+    if shrink_info is not None:
+        out["shrink"] = shrink_info
+    if prof is not None:
+        table, ctable, by_tag, prof_ms = prof
         out["kernels"] = table
+        out["kernel_classes"] = ctable
         out["kernel_stage_ms"] = by_tag
+        top = next((r for r in ctable if "algorithmic_GBps" in r), None)
         if top is not None:
-            pw = top["kernel"].startswith("an_pw")
+            traffic = measured_traffic(top["class"], args.model, PER_GPU_BATCH) if args.masks == "dense" else None
             out["roofline"] = {
-                "kernel": top["kernel"], "bound": "hbm", "achieved": top["algorithmic_GBps"],
-                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": top["frac_hbm"], "traffic": None,
-                "peak_source": peaks["source"] + " (sustained-step copy bandwidth)",
-                "share_of_step": top["share"],
-                "note": ("pointwise GEMM: arithmetic intensity below the machine balance, so HBM is the binding "
-                         "roof; tensor-pipe fraction %.4f of sustained bf16" % top["frac_tensor_sustained"]) if pw
-                else "depthwise: CUDA cores, HBM roof; FMA roof reported in DESIGN.md"}
+                "kernel": top["class"], "bound": "hbm", "achieved": top["algorithmic_GBps"],
+                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": top["frac_hbm"], "traffic": traffic,
+                "peak_source": peaks["source"] + " (STREAM-style copy, MEASURED_PEAKS.json)",
+                "share_of_step": top["share"], "algorithmic_bytes_per_step": int(top["algorithmic_GB"] * 1e9),
+                "accounting": "SURVEY 8(d): every tensor once per pass (forward, data gradient, weight gradient)",
+                "note": ("depthwise k3/5/7 family (an_dw_*): CUDA cores, HBM roof; k=7 is FP32-FMA bound at 49 FMA per "
+                         "4 bytes (FMA roof in DESIGN.md / profiles/r02_fma_probe.txt)") if top["class"] == "depthwise"
+                else "pointwise GEMMs: arithmetic intensity below the machine balance, HBM is the binding roof; "
+                     "tensor-pipe fraction %.4f of sustained bf16" % top["frac_tensor_sustained"]}
     if world == 1 and not args.no_cpu_baseline:
         try:
-            out["cpu_baseline"], _ = cpu_reference(2, 1, 32)
+            out["cpu_baseline"], _, _ = cpu_reference(kwargs, 2, 1, 64, budget_s=60.0)
         except Exception as ex:                         # the baseline must never sink the GPU number
             out["cpu_baseline"] = {"error": repr(ex)}
     print(json.dumps(out))

@@ -1,0 +1,155 @@
+// FP32 / packed-FMA issue-rate probe for sm_100a (B200): what the CUDA cores can sustain for the
+// depthwise kernels' inner loop.  Standalone: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o fma_probe fma_probe.cu
+// Prints FMA lanes per clock per SM (clock64-measured) and TFMA/s (event-measured) for
+//   ffma      : fma.rn.f32, 3 distinct register operands, 16 independent chains
+//   ffma2     : fma.rn.f32x2 (FFMA2), 3 distinct operands
+//   ffma2_w   : FFMA2 with the multiplier shared by 4 consecutive FMAs (the weight-reuse pattern)
+//   hfma2     : fma.rn.bf16x2
+//   dwmix     : FFMA2 + PRMT + LDS in the k7 depthwise ratio (196 : 20 : 10)
+// at 8 / 16 / 32 resident warps per SM.
+#include <cstdio>
+#include <cstdint>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); return 1; } } while (0)
+
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint32_t hfma2(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm volatile("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
+constexpr int ITERS = 2048;
+
+template <int MODE, int THREADS, int NA>
+__global__ void __launch_bounds__(THREADS) probe(float* out, long long* cycles, const float* in) {
+  __shared__ uint32_t sm[2048];
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x) sm[i] = 0x3f803f80u + i;
+  __syncthreads();
+  const float s = in[threadIdx.x & 31], s2 = in[(threadIdx.x + 7) & 31];
+  float acc_f[16];
+  unsigned long long acc2[16];
+  uint32_t acch[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    acc_f[i] = s * (i + 1);
+    float2 t = make_float2(s * (i + 1), s2 * (i + 2));
+    acc2[i] = *reinterpret_cast<unsigned long long*>(&t);
+    acch[i] = 0x3f803f80u + i;
+  }
+  float2 wv[4] = {make_float2(1.0001f, 0.9999f), make_float2(1.0002f, 0.9998f), make_float2(0.9997f, 1.0003f), make_float2(1.0004f, 0.9996f)};
+  unsigned long long w2[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { wv[i].x += s * 1e-9f; wv[i].y += s2 * 1e-9f; w2[i] = *reinterpret_cast<unsigned long long*>(&wv[i]); }
+  float2 xv[16];
+  unsigned long long x2[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { xv[i] = make_float2(1e-7f * (i + 1) + s * 1e-9f, 1e-7f * (i + 2) + s2 * 1e-9f); x2[i] = *reinterpret_cast<unsigned long long*>(&xv[i]); }
+  uint32_t hw = 0x3f803f81u + (uint32_t)(s != 0.f);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acch[i] += __float_as_uint(s2) & 1u;
+  const long long t0 = clock64();
+#pragma unroll 1
+  for (int it = 0; it < ITERS; ++it) {
+    if (MODE == 0) {
+#pragma unroll
+      for (int r = 0; r < 64 / NA; ++r)
+#pragma unroll
+        for (int i = 0; i < NA; ++i) acc_f[i] = fmaf(acc_f[i], wv[r & 3].x, xv[i].x);
+    } else if (MODE == 1) {
+#pragma unroll
+      for (int r = 0; r < 64 / NA; ++r)
+#pragma unroll
+        for (int i = 0; i < NA; ++i) acc2[i] = fma2(x2[(i + r) & (NA - 1)], w2[(i + r) & 3], acc2[i]);
+    } else if (MODE == 2) {
+#pragma unroll
+      for (int r = 0; r < 64 / NA; ++r)
+#pragma unroll
+        for (int i = 0; i < NA; ++i) acc2[i] = fma2(w2[r & 3], x2[i], acc2[i]);
+    } else if (MODE == 3) {
+#pragma unroll
+      for (int r = 0; r < 64 / NA; ++r)
+#pragma unroll
+        for (int i = 0; i < NA; ++i) acch[i] = hfma2(acch[i], hw, (uint32_t)(x2[i] >> 32));
+    } else {
+      // 64 FFMA2 : 6 PRMT : 3 LDS  (k7 depthwise: 196 : 20 : 10)
+      const uint32_t l0 = sm[(threadIdx.x + it) & 2047], l1 = sm[(threadIdx.x + it + 32) & 2047], l2 = sm[(threadIdx.x + it + 64) & 2047];
+      float2 u0 = make_float2(__uint_as_float(__byte_perm(l0, 0u, 0x1044)), __uint_as_float(__byte_perm(l0, 0u, 0x3244)));
+      float2 u1 = make_float2(__uint_as_float(__byte_perm(l1, 0u, 0x1044)), __uint_as_float(__byte_perm(l1, 0u, 0x3244)));
+      float2 u2 = make_float2(__uint_as_float(__byte_perm(l2, 0u, 0x1044)), __uint_as_float(__byte_perm(l2, 0u, 0x3244)));
+      x2[0] = *reinterpret_cast<unsigned long long*>(&u0);
+      x2[3] = *reinterpret_cast<unsigned long long*>(&u1);
+      x2[6] = *reinterpret_cast<unsigned long long*>(&u2);
+#pragma unroll
+      for (int r = 0; r < 64 / NA; ++r)
+#pragma unroll
+        for (int i = 0; i < NA; ++i) acc2[i] = fma2(w2[r & 3], x2[i], acc2[i]);
+    }
+  }
+  const long long t1 = clock64();
+  float r = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    float2 t = *reinterpret_cast<float2*>(&acc2[i]);
+    r += acc_f[i] + t.x + t.y + __uint_as_float(acch[i]);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+  if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+template <int MODE, int THREADS, int NA>
+int run(const char* name, int lanes_per_inst, int sms, float* out, long long* cyc, const float* in) {
+  const int threads = THREADS;
+  cudaEvent_t a, b;
+  CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+  probe<MODE, THREADS, NA><<<sms, threads>>>(out, cyc, in);
+  CK(cudaDeviceSynchronize());
+  CK(cudaEventRecord(a));
+  probe<MODE, THREADS, NA><<<sms, threads>>>(out, cyc, in);
+  CK(cudaEventRecord(b));
+  CK(cudaDeviceSynchronize());
+  float ms;
+  CK(cudaEventElapsedTime(&ms, a, b));
+  long long h[1024];
+  CK(cudaMemcpy(h, cyc, sizeof(long long) * sms, cudaMemcpyDeviceToHost));
+  long long mx = 0;
+  for (int i = 0; i < sms; ++i) mx = h[i] > mx ? h[i] : mx;
+  const double fmas_per_sm = (double)ITERS * 64 * lanes_per_inst * threads;      // 64 instr/iter/thread
+  printf("%-8s warps/SM=%2d ILP=%2d  FMA/clk/SM=%7.1f  inst/clk/SMSP=%5.3f  TFMA/s=%6.2f  (%.3f ms, %lld clk)\n", name,
+         threads / 32, NA, fmas_per_sm * 32 / mx, (double)ITERS * 64 * (threads / 32) / 4.0 / mx,
+         fmas_per_sm * 32 * sms / (ms * 1e-3) / 1e12, ms, mx);
+  return 0;
+}
+
+template <int THREADS, int NA>
+int run_all(int sms, float* out, long long* cyc, const float* in) {
+  if (run<0, THREADS, NA>("ffma", 1, sms, out, cyc, in)) return 1;
+  if (run<1, THREADS, NA>("ffma2", 2, sms, out, cyc, in)) return 1;
+  if (run<2, THREADS, NA>("ffma2_w", 2, sms, out, cyc, in)) return 1;
+  if (run<3, THREADS, NA>("hfma2", 2, sms, out, cyc, in)) return 1;
+  if (run<4, THREADS, NA>("dwmix", 2, sms, out, cyc, in)) return 1;
+  return 0;
+}
+
+int main() {
+  int dev = 0, sms = 0;
+  CK(cudaSetDevice(dev));
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  float *out, *in; long long* cyc;
+  CK(cudaMalloc(&out, sizeof(float) * sms * 1024));
+  CK(cudaMalloc(&in, sizeof(float) * 32));
+  CK(cudaMemset(in, 0, sizeof(float) * 32));
+  CK(cudaMalloc(&cyc, sizeof(long long) * 1024));
+  printf("SMs=%d  (FP32 peak = 128 FMA/clk/SM if every SMSP issues one 32-lane FFMA per clock)\n", sms);
+  if (run_all<256, 16>(sms, out, cyc, in)) return 1;
+  if (run_all<256, 8>(sms, out, cyc, in)) return 1;
+  if (run_all<512, 16>(sms, out, cyc, in)) return 1;
+  if (run_all<1024, 8>(sms, out, cyc, in)) return 1;
+  return 0;
+}

@@ -1,0 +1,113 @@
+"""Two-rank NCCL parity of the data-parallel step (utils/distributed.py:131-161,
+train.py:184-185).  Needs >= 2 GPUs (`gpurun --gpus 2`); skipped on a single-GPU box.
+
+Checks, for the eager (bucketed, backward-overlapped all-reduce), the split-graph and -- when
+AN_TEST_GRAPH_NCCL=1 -- the single-graph-with-captured-NCCL modes:
+  * after the all-reduce the gradient arena is BIT-EQUAL on both ranks, and so are the parameters
+    after the optimizer step;
+  * the 2-rank step equals the 1-rank step over the same global batch with per-GPU BatchNorm
+    (= two micro-batches accumulated on one GPU, Trainer.step_accum): parameters bit-equal, mean loss
+    equal;
+  * replicas start identical (AllReduceDistributedDataParallel broadcasts rank 0's arenas).
+"""
+import os
+import sys
+import traceback
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+G = os.path.join(ROOT, "tests", "golden")
+
+
+def _worker(rank, world, port, mode, errq):
+    try:
+        import torch.distributed as dist
+        from atomnas_b200 import distributed as udist
+        from atomnas_b200 import mobilenet_supernet as ms
+        from atomnas_b200 import prune
+        from atomnas_b200.trainer import Trainer
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), LOCAL_RANK=str(rank),
+                          WORLD_SIZE=str(world))
+        if mode == "graph_nccl":
+            os.environ["AN_GRAPH_NCCL"] = "1"
+        udist.init_dist()
+        g = torch.load(os.path.join(G, "tiny_supernet_train.pt"), weights_only=False)
+
+        def build(perturb):
+            m = ms.MobileNetV2(**g["kwargs"], input_size=g["input_size"])
+            m.load_state_dict(g["state0"])
+            if perturb:                                # ranks != 0 start wrong; the wrapper must fix it
+                with torch.no_grad():
+                    for p in m.parameters():
+                        p.add_(0.01 * rank)
+            return m.cuda().train()
+
+        def trainer(m, graph, distributed=True):
+            prune.profile_macs(m, g["input_size"])
+            info = prune.get_bn_to_prune(m, {"bn_prune_filter": "expansion_only_skip_expand1"}, verbose=False)
+            return Trainer(m, lr=0.016, weight_decay=1e-5, label_smoothing=0.1, ema_decay=0.9999 ** 0.5,
+                           prune_penalties=list(zip(info.weight, info.penalty)), use_cuda_graph=graph,
+                           distributed=distributed)
+
+        model = build(True)
+        wrapped = udist.AllReduceDistributedDataParallel(model)
+        assert wrapped.module is model
+        tr = trainer(model, graph=(mode != "eager"))
+        recs = g["steps"]
+        mine = [(recs[(2 * i + rank) % len(recs)]["x"].cuda(), recs[(2 * i + rank) % len(recs)]["y"].cuda()) for i in range(3)]
+        both = [[(recs[(2 * i + r) % len(recs)]["x"].cuda(), recs[(2 * i + r) % len(recs)]["y"].cuda()) for r in range(world)]
+                for i in range(3)]
+        ref_model = build(False)
+        ref = trainer(ref_model, graph=(mode != "eager"), distributed=False)
+        for i in range(3):                              # graph modes: eager warm-up, capture, replay
+            loss = tr.step(mine[i][0], mine[i][1], rho=1e-4).mean()
+            gl = [torch.empty_like(tr.eng.G) for _ in range(world)]
+            dist.all_gather(gl, tr.eng.G)
+            assert torch.equal(gl[0], gl[1]), "gradient arenas differ across ranks after the all-reduce (step %d)" % i
+            pl = [torch.empty_like(tr.eng.P) for _ in range(world)]
+            dist.all_gather(pl, tr.eng.P)
+            assert torch.equal(pl[0], pl[1]), "parameters differ across ranks (step %d)" % i
+            ll = [torch.empty_like(loss) for _ in range(world)]
+            dist.all_gather(ll, loss)
+            loss_ref = ref.step_accum(both[i], rho=1e-4)
+            assert torch.equal(ref.eng.P, tr.eng.P), "2-rank step != 1-rank accumulated step (step %d): max diff %g" % (
+                i, (ref.eng.P - tr.eng.P).abs().max().item())
+            assert abs((ll[0] + ll[1]).item() / 2 - loss_ref.item()) <= 1e-6
+        # explicit train.py-style calls on the drop-in surface
+        udist.allreduce_bn(wrapped)
+        sl = [torch.empty_like(tr.eng.S) for _ in range(world)]
+        dist.all_gather(sl, tr.eng.S)
+        assert torch.equal(sl[0], sl[1])
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:
+        errq.put("rank %d (%s):\n%s" % (rank, mode, traceback.format_exc()))
+        raise
+
+
+@pytest.mark.parametrize("mode", ["eager", "graph_split"] + (["graph_nccl"] if os.environ.get("AN_TEST_GRAPH_NCCL") == "1" else []))
+def test_two_rank_nccl_step_parity(mode):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    errq = ctx.Queue()
+    port = 29500 + (os.getpid() % 1000) + {"eager": 0, "graph_split": 1, "graph_nccl": 2}[mode]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, mode, errq)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+    errs = []
+    while not errq.empty():
+        errs.append(errq.get())
+    for p in procs:
+        if p.is_alive():
+            p.kill()
+            errs.append("timeout")
+    assert not errs and all(p.exitcode == 0 for p in procs), "\n".join(errs)
