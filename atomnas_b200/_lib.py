@@ -107,6 +107,14 @@ SIGNATURES = {
     "an_reg_losses": (c_int, [c_fp, c_fp, c_fp, c_ll, c_fp, c_vp]),
     "an_refresh_weights": (c_int, [c_vp, c_int, c_ll, c_fp, c_vp, c_fp, c_vp]),
     "an_gather_rows": (c_int, [c_fp, c_vp, c_ll, c_ll, c_fp, c_vp]),
+    "an_se_pool": (c_int, [c_vp, c_ll, c_vp, c_ll, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_fp, c_vp]),
+    "an_se_gate": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_vp, c_int, c_int, c_int, c_int, c_int, c_fp, c_fp, c_vp]),
+    "an_se_scale": (c_int, [c_vp, c_ll, c_fp, c_fp, c_int, c_fp, c_int, c_int, c_int, c_vp, c_ll, c_vp]),
+    "an_se_gate_bwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int,
+                               c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_vp]),
+    "an_se_bwd_apply_rows": (c_int, [c_ll, c_int]),
+    "an_se_bwd_apply": (c_int, [c_vp, c_ll, c_vp, c_ll, c_fp, c_fp, c_fp, c_fp, c_int, c_fp, c_fp, c_int, c_int,
+                                c_int, c_vp, c_ll, c_fp, c_vp]),
 }
 
 _lib = None

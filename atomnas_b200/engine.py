@@ -356,8 +356,7 @@ class Engine(object):
             bb.M, bb.Mo = M, Mo
             if p.branches:
                 if p.expand:
-                    bb.e_raw = bf16(M, p.Kh)
-                    bb.u = bf16(M, p.Kh)          # act(bn(e_raw)): the depthwise operand, TMA-staged
+                    bb.e_raw = bf16(M, p.Kh)      # raw expand output: the depthwise kernels apply BN + act on load
                     part_max = max(part_max, K.pw_gemm_stats_rows(M, p.Kh) * 2 * p.Kh)
                     wpart_max = max(wpart_max, K.pw_wgrad_splits(M, p.Kh, p.inp) * p.Kh * p.inp)
                     big_e = max(big_e, M * p.Kh)
@@ -517,17 +516,18 @@ class Engine(object):
             TAG[0] = "fwd.expand"
             K.pw_gemm(x, self.W16[p.we16:], bb.e_raw, M, p.Kh, p.inp, stats_part=stats)
             self._bn_fwd(p.bn_e, part, K.pw_gemm_stats_rows(M, p.Kh), M, training)
-            # materialise the depthwise operand once (bf16): the dw kernels are FMA-issue bound and
-            # stage it with TMA, so the BN-apply + activation must not ride on their load path
-            K.affine_act(bb.e_raw, bb.u, M, p.Kh, ld1=p.Kh, ldo=p.Kh, a1=self.bn_vec(p.bn_e, "scale"),
-                         a3=self.bn_vec(p.bn_e, "shift"), act=p.act)
-            src, ld_src = bb.u, p.Kh
+            # the depthwise kernels read the RAW expand output and apply BN + activation on load
+            # (csrc/dw2.cu): the activated 6x-expanded tensor is never written to HBM
+            src, ld_src = bb.e_raw, p.Kh
+            x_scale, x_shift = self.bn_vec(p.bn_e, "scale"), self.bn_vec(p.bn_e, "shift")
         else:
-            src, ld_src = x, p.inp
+            src, ld_src, x_scale, x_shift = x, p.inp, None, None
         for br in p.branches:
             TAG[0] = "fwd.dw%d" % br.k
             K.dw_fwd(src[:, br.off:], bb.d_raw[:, br.off:], self.W32[br.wd32:], B, bb.hin, bb.win, br.hp,
-                     br.k, p.stride, ldx=ld_src, ldy=p.Kh, act=p.act, stats_part=stats)
+                     br.k, p.stride, ldx=ld_src, ldy=p.Kh, act=p.act if p.expand else 0, stats_part=stats,
+                     scale=None if x_scale is None else x_scale[br.off:],
+                     shift=None if x_shift is None else x_shift[br.off:])
             self._bn_fwd(p.bn_d, part, K.dw_fwd_stats_rows(B, br.hp, bb.ho, bb.wo, br.k, p.stride, False), Mo,
                          training, C=br.hp, off=br.off)
         TAG[0] = "fwd.project"
@@ -640,7 +640,7 @@ class Engine(object):
         K.affine_act(g_d, g_d, Mo, p.Kh, ld1=p.Kh, ldo=p.Kh, x2=bb.d_raw, ld2=p.Kh,
                      a1=self.bn_vec(p.bn_d, "ca"), a2=self.bn_vec(p.bn_d, "cb"), a3=self.bn_vec(p.bn_d, "cc"))
         if p.expand:
-            usrc, ld_src = bb.u, p.Kh              # activated input (forward operand)
+            usrc, ld_src = bb.e_raw, p.Kh          # raw expand output; BN + act re-applied on load
             e_scale, e_shift = self.bn_vec(p.bn_e, "scale"), self.bn_vec(p.bn_e, "shift")
             e_mean, e_rstd = self.bn_vec(p.bn_e, "mean"), self.bn_vec(p.bn_e, "rstd")
             eraw, ge, ld_ge = bb.e_raw, bf.g_e, p.Kh
@@ -655,11 +655,11 @@ class Engine(object):
             o = br.off
             TAG[0] = "bwd.dw%d_wgrad" % br.k
             if br.hp == br.h:
-                K.dw_bwd_weight(g_d[o:], bb.d_raw[:, o:], usrc[:, o:], None, None, None, None, None, 0, wpart,
-                                G[br.wd_off:], B, bb.hin, bb.win, br.hp, br.k, p.stride, ldg=p.Kh, ldd=p.Kh,
-                                lde=ld_src)
+                K.dw_bwd_weight(g_d[o:], bb.d_raw[:, o:], usrc[:, o:], None, None, None, sl(e_scale, br),
+                                sl(e_shift, br), act if p.expand else 0, wpart, G[br.wd_off:], B, bb.hin, bb.win,
+                                br.hp, br.k, p.stride, ldg=p.Kh, ldd=p.Kh, lde=ld_src)
             else:
-                self._dw_wgrad_padded(p, bb, br, g_d, usrc, ld_src, B, wpart)
+                self._dw_wgrad_padded(p, bb, br, g_d, usrc, ld_src, B, wpart, sl(e_scale, br), sl(e_shift, br))
             TAG[0] = "bwd.dw%d_dgrad" % br.k
             K.dw_bwd_data(g_d[o:], bb.d_raw[:, o:], eraw[:, o:], ge[o:], self.W32[br.wd32:], None, None, None,
                           sl(e_scale, br), sl(e_shift, br), sl(e_mean, br), sl(e_rstd, br),
@@ -682,13 +682,14 @@ class Engine(object):
         K.pw_gemm(ge, self.W16[p.weT16:], dx, M, p.inp, p.Kh, x2=bb.e_raw, a_mode=2, a1=eca, a2=ecb, a3=ecc,
                   epi_mode=2, r=dy if p.res else None, ldr=p.oup)
 
-    def _dw_wgrad_padded(self, p, bb, br, g_d, usrc, ld_src, B, wpart):
+    def _dw_wgrad_padded(self, p, bb, br, g_d, usrc, ld_src, B, wpart, e_scale, e_shift):
         """Depthwise weight gradient of a branch whose width is not a multiple of 8: run on the
         padded slot into scratch, then keep the first h rows (pad rows are exactly zero)."""
         o = br.off
         tmp = next(iter(self.bufs.values())).dw_tmp          # sized at plan time (graph safe)
-        K.dw_bwd_weight(g_d[o:], bb.d_raw[:, o:], usrc[:, o:], None, None, None, None, None, 0, wpart, tmp, B,
-                        bb.hin, bb.win, br.hp, br.k, p.stride, ldg=p.Kh, ldd=p.Kh, lde=ld_src)
+        K.dw_bwd_weight(g_d[o:], bb.d_raw[:, o:], usrc[:, o:], None, None, None, e_scale, e_shift,
+                        p.act if p.expand else 0, wpart, tmp, B, bb.hin, bb.win, br.hp, br.k, p.stride, ldg=p.Kh,
+                        ldd=p.Kh, lde=ld_src)
         n = br.h * br.k * br.k
         self.G[br.wd_off:br.wd_off + n].copy_(tmp[:n])
 

@@ -243,3 +243,38 @@ def act_bwd_reduce(dy, x, scale, shift, mean, rstd, act, g, part, M, C, *, ldy, 
 def sum_rows(part, rows, row_stride, n, dst):
     L.check(L.lib().an_sum_rows(_c(part), rows, row_stride, n, _c(dst), L.stream_ptr()),
             "an_sum_rows")
+
+
+# ------------------------------------------------------------------------------------------------
+# squeeze-and-excitation (fused block)
+# ------------------------------------------------------------------------------------------------
+def se_pool(x, ldx, scale, shift, act, B, HW, C, out, D=None, ldD=0, mean=True):
+    L.check(L.lib().an_se_pool(_c(x), ldx, _c(D), ldD, _c(scale), _c(shift), act, B, HW, C, 1 if mean else 0,
+                               _c(out), L.stream_ptr()), "an_se_pool")
+
+
+def se_gate(pooled, W1, b1, W2, b2, chmap, act, B, C, total, mid, hpre, gate):
+    L.check(L.lib().an_se_gate(_c(pooled), _c(W1), _c(b1), _c(W2), _c(b2), _c(chmap), act, B, C, total, mid,
+                               _c(hpre), _c(gate), L.stream_ptr()), "an_se_gate")
+
+
+def se_scale(x, ldx, scale, shift, act, gate, B, HW, C, out, ldo):
+    L.check(L.lib().an_se_scale(_c(x), ldx, _c(scale), _c(shift), act, _c(gate), B, HW, C, _c(out), ldo,
+                                L.stream_ptr()), "an_se_scale")
+
+
+def se_gate_bwd(dgate, gate, hpre, pooled, W1, W2, chmap, inv_map, act, B, C, total, mid, dz, dh, ds, dW1, db1,
+                dW2, db2):
+    L.check(L.lib().an_se_gate_bwd(_c(dgate), _c(gate), _c(hpre), _c(pooled), _c(W1), _c(W2), _c(chmap),
+                                   _c(inv_map), act, B, C, total, mid, _c(dz), _c(dh), _c(ds), _c(dW1), _c(db1),
+                                   _c(dW2), _c(db2), L.stream_ptr()), "an_se_gate_bwd")
+
+
+def se_bwd_apply_rows(M, C):
+    return L.lib().an_se_bwd_apply_rows(M, C)
+
+
+def se_bwd_apply(D, ldD, x, ldx, scale, shift, mean, rstd, act, gate, ds, B, HW, C, g, ldg, part):
+    L.check(L.lib().an_se_bwd_apply(_c(D), ldD, _c(x), ldx, _c(scale), _c(shift), _c(mean), _c(rstd), act,
+                                    _c(gate), _c(ds), B, HW, C, _c(g), ldg, _c(part), L.stream_ptr()),
+            "an_se_bwd_apply")

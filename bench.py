@@ -280,30 +280,40 @@ def cpu_reference(kwargs, steps, warmup, batch, budget_s=200.0):
         run(x, y)
         return time.perf_counter() - t0
 
-    # thread count: the oneDNN depthwise/1x1 primitives at this batch stop scaling well before a
-    # large host's core count, so take the fastest of {all, 1/2, 1/4, 1/8, 1/16} of the cores
-    x, y = data(batch)
-    best_t, best_n = None, cores
+    # Thread count: the oneDNN depthwise / 1x1 primitives at this batch stop scaling well before a
+    # large host's core count (and oversubscribed runs are many times slower), so probe ASCENDING
+    # thread counts {cores/16 .. cores} on a small batch and stop at the first one that is slower
+    # or when 35 % of the time budget is gone.  Everything below is bounded by `budget_s`.
     t_start = time.perf_counter()
-    for n in sorted({max(min(cores, 8), cores // d) for d in (1, 2, 4, 8, 16)}, reverse=True):
+    xs, ys = data(min(16, batch))
+    best_t, best_n = None, max(1, min(cores, 8))
+    for n in sorted({max(min(cores, 8), cores // d) for d in (16, 8, 4, 2, 1)}):
         torch.set_num_threads(n)
-        one(x, y)                                      # primitive creation per shape happens here
-        t = one(x, y)
+        one(xs, ys)                                    # primitive creation per shape happens here
+        t = one(xs, ys)
         if best_t is None or t < best_t:
             best_t, best_n = t, n
-        if time.perf_counter() - t_start > 0.4 * budget_s:
+        elif t > 1.15 * best_t:
+            break
+        if time.perf_counter() - t_start > 0.35 * budget_s:
             break
     torch.set_num_threads(best_n)
-    # bounded sample: shrink the per-step batch until warmup + steps fit the budget
-    while batch > 8 and (steps + warmup) * best_t * 1.1 > 0.6 * budget_s:
+    per_image = best_t / xs.shape[0]
+    left = budget_s - (time.perf_counter() - t_start)
+    # bounded sample: the largest batch in {64, 32, 16, 8} whose warm-up + steps fit what is left
+    while batch > 8 and (steps + warmup + 1) * per_image * batch * 1.15 > left:
         batch //= 2
-        x, y = data(batch)
-        one(x, y)
-        best_t = one(x, y)
+    x, y = data(batch)
+    one(x, y)                                          # shapes of this batch
     for _ in range(warmup):
         one(x, y)
-    times = [one(x, y) for _ in range(steps)]
+    times = []
+    for _ in range(steps):
+        times.append(one(x, y))
+        if time.perf_counter() - t_start > 1.5 * budget_s:      # hard stop: report what was measured
+            break
     sec = sum(times) / len(times)
+    steps = len(times)
     what = ("unmodified reference modules (oracle/_ref: models.mobilenet_supernet, utils.rmsprop, utils.optim, "
             "utils.prune), fp32 as shipped") if kind == "reference" else "oracle port (fp32 torch CPU ops)"
     return {"value": batch / sec, "unit": "images/sec", "cores": best_n, "host_cores": cores, "kind": kind,

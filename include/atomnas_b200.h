@@ -106,15 +106,17 @@ int an_wgrad_reduce(const float* partials, int splits, int Cbig, int Csmall, int
  * and its autograd backward.  Pointers are pre-offset to the branch's first channel; C is the
  * branch width, ld* the full row pitch of the (branch-fused) tensor.
  *   forward : y = dwconv(act(scale*x + shift)) (scale == NULL: x used as is), BN partials of y
- *   bwd_data: dd = ca*g + cb*draw + cc; du = dwconv^T(dd);
+ *   bwd_data: du = dwconv^T(g);   g = dd, the BN-backward-applied gradient (an_affine_act)
  *             ge = du * act'(e_scale*eraw + e_shift); partials sum(ge), sum(ge*xhat_e)
- *   bwd_weight: dW[c][kr][kc] = sum dd * act(e_scale*eraw + e_shift) (master layout [C,1,k,k])
+ *   bwd_weight: dW[c][kr][kc] = sum g * act(e_scale*eraw + e_shift) (master layout [C,1,k,k];
+ *             e_scale == NULL: eraw is the already activated input)
  * w is tap-major fp32 [k*k][C] (written by an_refresh_weights).
- * Operands may be passed already materialised (scale == NULL: x is the activated input; ca == NULL:
- * g is dd; e_scale == NULL in bwd_weight: eraw is the activated input).  Materialised operands
- * (both strides) take the TMA-staged row-streaming kernels (csrc/dw_stream.cu) -- the engine's hot
- * path; the on-load transforms run on the tile kernels (csrc/dw_conv.cu).  The `fused` flag of the
- * *_rows helpers says which variant the partial buffers are sized for (fused = 0: materialised).
+ * The producer's BatchNorm + activation is applied ON LOAD by the forward and weight-gradient
+ * kernels (scale / e_scale != NULL), so the activated operand is never materialised in HBM.
+ * Row-streaming kernels: csrc/dw2.cu (forward, stride-1 data gradient, weight gradient) and
+ * csrc/dw_stream.cu (stride-2 data gradient).  ca / cb / cc must be NULL (the on-load BN-backward
+ * transform of g was removed together with the tile kernels); draw is unused.  The `fused`
+ * argument of the *_rows helpers is ignored (one kernel family serves both operand forms).
  * ------------------------------------------------------------------------------------------ */
 typedef struct {
   const void* x; long long ldx;
@@ -231,6 +233,38 @@ int an_refresh_weights(const void* table, int n_entries, long long total_tiles, 
                        void* dst_bf16, float* dst_f32, void* stream);
 int an_gather_rows(const float* src, const long long* idx, long long n_out, long long inner,
                    float* dst, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Squeeze-and-Excitation of the fused atomic block (AtomNAS-A+/B+/C+):
+ * SqueezeAndExcitation models/mobilenet_base.py:93-117 as used by
+ * InvertedResidualChannelsFused.forward :256-267, and its autograd backward.
+ *   v = act(scale*x + shift) (x = raw depthwise output, branch-fused NHWC bf16 [B*HW, C]);
+ *   an_se_pool   : out[b,c] = mean_hw v           (D == NULL, mean = 1)
+ *                  out[b,c] = sum_hw D*v          (D != NULL, mean = 0: d loss / d gate)
+ *   an_se_gate   : h = W1 s + b1, a = act(h), z = W2 a + b2, gate = sigmoid(z); hpre = h is kept
+ *   an_se_scale  : out = v * gate[sample]         (the projection GEMM's A operand)
+ *   an_se_gate_bwd: dz, dh, ds (= d loss / d pooled) per sample, and the FC weight / bias gradients
+ *                  summed over the batch in fixed order
+ *   an_se_bwd_apply: g = (D*gate + ds/HW) * act'(scale*x + shift) -> bf16, partials sum(g), sum(g*xhat)
+ * W1 [mid, total], W2 [total, mid], b1 [mid], b2 [total]: fp32 master layout (nn.Conv2d 1x1 with
+ * bias); chmap[C] = master channel of a padded channel or -1, inv_map[total] its inverse.
+ * ------------------------------------------------------------------------------------------ */
+int an_se_pool(const void* x, long long ldx, const void* D, long long ldD, const float* scale,
+               const float* shift, int act, int B, int HW, int C, int mean, float* out, void* stream);
+int an_se_gate(const float* pooled, const float* W1, const float* b1, const float* W2, const float* b2,
+               const int* chmap, int act, int B, int C, int total, int mid, float* hpre, float* gate,
+               void* stream);
+int an_se_scale(const void* x, long long ldx, const float* scale, const float* shift, int act,
+                const float* gate, int B, int HW, int C, void* out, long long ldo, void* stream);
+int an_se_gate_bwd(const float* dgate, const float* gate, const float* hpre, const float* pooled,
+                   const float* W1, const float* W2, const int* chmap, const int* inv_map, int act, int B,
+                   int C, int total, int mid, float* dz, float* dh, float* ds, float* dW1, float* db1,
+                   float* dW2, float* db2, void* stream);
+int an_se_bwd_apply_rows(long long M, int C);
+int an_se_bwd_apply(const void* D, long long ldD, const void* x, long long ldx, const float* scale,
+                    const float* shift, const float* mean, const float* rstd, int act, const float* gate,
+                    const float* ds, int B, int HW, int C, void* g, long long ldg, float* stats_part,
+                    void* stream);
 
 #ifdef __cplusplus
 }

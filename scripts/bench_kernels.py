@@ -1,7 +1,9 @@
 """Kernel / shape sweep (BASELINE.json configs[4]): every (C, H, k, stride) depthwise layer and every
 pointwise GEMM shape of the AtomNAS-C supernet at 256 images, each kernel timed alone with CUDA
 events on rotating buffers larger than L2, reported as algorithmic GB/s and fraction of the measured
-HBM peak.   python scripts/bench_kernels.py [dw|pw|all] [batch] [--json out.json]
+HBM peak.   python scripts/bench_kernels.py [dw|pw|all] [batch] [--json out.json] [--res 224] [--plain]
+--res R scales every feature map by R/224 (BASELINE config 5: 128 / 160 / 192 / 224); --plain feeds
+the depthwise kernels materialised operands instead of BN + activation on load (the engine's path).
 """
 import json
 import os
@@ -41,9 +43,10 @@ def nrot_for(nbytes):
     return max(2, min(8, int(400e6 // max(nbytes, 1)) + 1))
 
 
-def dw_sweep(B, out):
+def dw_sweep(B, out, res=224, plain=False):
     seen = set()
     for cin, h, H, stride, cout in BLOCKS:
+        H = H * res // 224
         for k in (3, 5, 7):
             key = (h, H, k, stride)
             if key in seen:
@@ -66,22 +69,23 @@ def dw_sweep(B, out):
             wpart = torch.empty(K.dw_bwd_weight_rows(B, C, H, H, k, stride, False) * k * k * C + 8, device=DEV)
 
             def f_fwd(i):
-                K.dw_fwd(x[i], y[i], w, B, H, H, C, k, stride, ldx=C, ldy=C, act=1, stats_part=part)
+                K.dw_fwd(x[i], y[i], w, B, H, H, C, k, stride, ldx=C, ldy=C, act=1, stats_part=part,
+                         scale=None if plain else sc, shift=None if plain else sh)
 
             def f_bd(i):
                 K.dw_bwd_data(dd[i], y[i], x[i], ge[i], w, None, None, None, sc, sh, sh, sc, part, 1,
                               B, H, H, C, k, stride, ldg=C, ldd=C, lde=C, ldge=C)
 
             def f_bw(i):
-                K.dw_bwd_weight(dd[i], y[i], x[i], None, None, None, None, None, 0, wpart, dwt,
-                                B, H, H, C, k, stride, ldg=C, ldd=C, lde=C)
+                K.dw_bwd_weight(dd[i], y[i], x[i], None, None, None, None if plain else sc, None if plain else sh,
+                                0 if plain else 1, wpart, dwt, B, H, H, C, k, stride, ldg=C, ldd=C, lde=C)
 
             for name, fn, nbytes in (("dw_fwd", f_fwd, 2 * (M + Mo) * C), ("dw_bwd_data", f_bd, 2 * (Mo + 2 * M) * C),
                                      ("dw_bwd_weight", f_bw, 2 * (Mo + M) * C)):
                 ms = timeit(fn, nr)
                 gbs = nbytes / ms / 1e6
                 gfma = Mo * C * k * k / ms / 1e6
-                row = {"kernel": name, "C": C, "H": H, "k": k, "stride": stride, "ms": round(ms, 4),
+                row = {"kernel": name, "C": C, "H": H, "k": k, "stride": stride, "res": res, "ms": round(ms, 4),
                        "GBps": round(gbs, 1), "frac_hbm": round(gbs / PEAK, 3), "GFMAps": round(gfma, 1)}
                 out.append(row)
                 print(row, flush=True)
@@ -138,8 +142,9 @@ def main():
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     B = int(sys.argv[2]) if len(sys.argv) > 2 else 256
     out = []
+    res = int(sys.argv[sys.argv.index("--res") + 1]) if "--res" in sys.argv else 224
     if which in ("dw", "all"):
-        dw_sweep(B, out)
+        dw_sweep(B, out, res, "--plain" in sys.argv)
     if which in ("pw", "all"):
         pw_sweep(B, out)
     tot = {}
@@ -148,7 +153,8 @@ def main():
     print("sum of ms per kernel family (one launch per distinct shape):", {k: round(v, 3) for k, v in tot.items()})
     if "--json" in sys.argv:
         with open(sys.argv[sys.argv.index("--json") + 1], "w") as f:
-            json.dump({"batch": B, "peak_hbm_gbs": PEAK, "rows": out}, f, indent=1)
+            json.dump({"batch": B, "res": res, "peak_hbm_gbs": PEAK, "rows": out,
+                       "dw_occupancy": os.environ.get("AN_DW_OCC", "default")}, f, indent=1)
 
 
 if __name__ == "__main__":

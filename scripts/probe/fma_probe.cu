@@ -122,8 +122,8 @@ int run(const char* name, int lanes_per_inst, int sms, float* out, long long* cy
   for (int i = 0; i < sms; ++i) mx = h[i] > mx ? h[i] : mx;
   const double fmas_per_sm = (double)ITERS * 64 * lanes_per_inst * threads;      // 64 instr/iter/thread
   printf("%-8s warps/SM=%2d ILP=%2d  FMA/clk/SM=%7.1f  inst/clk/SMSP=%5.3f  TFMA/s=%6.2f  (%.3f ms, %lld clk)\n", name,
-         threads / 32, NA, fmas_per_sm * 32 / mx, (double)ITERS * 64 * (threads / 32) / 4.0 / mx,
-         fmas_per_sm * 32 * sms / (ms * 1e-3) / 1e12, ms, mx);
+         threads / 32, NA, fmas_per_sm / mx, (double)ITERS * 64 * (threads / 32) / 4.0 / mx,
+         fmas_per_sm * sms / (ms * 1e-3) / 1e12, ms, mx);
   return 0;
 }
 

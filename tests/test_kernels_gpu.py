@@ -57,8 +57,8 @@ DW_CASES = [
 ]
 
 
-@pytest.mark.parametrize("B,H,W,Ct,co,C,k,s", DW_CASES)
-@pytest.mark.parametrize("act", [1, 3])
+@pytest.mark.parametrize("B,H,W,Ct,co,C,k,s", DW_CASES + [(3, 56, 56, 144, 0, 144, 7, 1), (3, 14, 14, 480, 0, 480, 5, 1), (2, 56, 56, 144, 0, 144, 5, 2)])
+@pytest.mark.parametrize("act", [0, 1, 2, 3])
 def test_dw_forward(B, H, W, Ct, co, C, k, s, act):
     torch.manual_seed(B * H + C + k)
     x = bf(torch.randn(B, H, W, Ct, device=DEV))
@@ -71,7 +71,7 @@ def test_dw_forward(B, H, W, Ct, co, C, k, s, act):
     part = torch.full((rows, 2, C), float("nan"), device=DEV)
     K.dw_fwd(x[..., co:], y[..., co:], tap_major(w), B, H, W, C, k, s, ldx=Ct, ldy=Ct,
              scale=scale[co:], shift=shift[co:], act=act, stats_part=part)
-    u = bf(act_f(scale[co:co + C] * x[..., co:co + C].float() + shift[co:co + C], act))
+    u = act_f(scale[co:co + C] * x[..., co:co + C].float() + shift[co:co + C], act)     # fp32 on load
     ref = nhwc(F.conv2d(nchw(u), w, None, s, (k - 1) // 2, 1, C))
     got = y[..., co:co + C].float()
     assert (got - ref).abs().max().item() <= 1e-2 * ref.abs().max().item() + 1e-3
@@ -82,12 +82,12 @@ def test_dw_forward(B, H, W, Ct, co, C, k, s, act):
     torch.testing.assert_close(st[1], (got * got).sum((0, 1, 2)), rtol=1e-3, atol=0.05)
 
 
-@pytest.mark.parametrize("B,H,W,Ct,co,C,k,s", DW_CASES)
-def test_dw_backward(B, H, W, Ct, co, C, k, s):
+@pytest.mark.parametrize("B,H,W,Ct,co,C,k,s", DW_CASES + [(3, 56, 56, 144, 0, 144, 7, 1), (2, 56, 56, 144, 0, 144, 5, 2)])
+@pytest.mark.parametrize("act", [1, 2, 3])
+def test_dw_backward(B, H, W, Ct, co, C, k, s, act):
     if s == 2 and (H % 2 or W % 2):
         pytest.skip("stride 2 needs even sizes")
     torch.manual_seed(B + H + C + k + s)
-    act = 1
     Ho, Wo = K.dw_out_hw(H, W, k, s)
     eraw = bf(torch.randn(B, H, W, Ct, device=DEV))
     g = bf(torch.randn(B, Ho, Wo, Ct, device=DEV))
@@ -99,15 +99,22 @@ def test_dw_backward(B, H, W, Ct, co, C, k, s):
     em = torch.randn(Ct, device=DEV) * 0.1
     er = torch.rand(Ct, device=DEV) + 0.5
     sl = slice(co, co + C)
+    # dd = BN-backward applied gradient, materialised by the element-wise kernel (the depthwise
+    # kernels take it as their `g` operand; the producer's BN + activation is applied ON LOAD)
+    ddf = torch.zeros(B, Ho, Wo, Ct, device=DEV, dtype=torch.bfloat16)
+    K.affine_act(g[..., co:], ddf[..., co:], B * Ho * Wo, C, ld1=Ct, ldo=Ct, x2=draw[..., co:], ld2=Ct,
+                 a1=ca[co:], a2=cb[co:], a3=cc[co:])
     dd = bf(ca[sl] * g[..., sl].float() + cb[sl] * draw[..., sl].float() + cc[sl])
+    assert (ddf[..., sl].float() - dd.float()).abs().max().item() <= 1e-2 * dd.float().abs().max().item()
+    dd = ddf[..., sl]
     pre = es[sl] * eraw[..., sl].float() + eh[sl]
     u = bf(act_f(pre, act))
     # ---- data gradient
     ge = torch.zeros(B, H, W, Ct, device=DEV, dtype=torch.bfloat16)
     rows = K.dw_bwd_data_stats_rows(B, C, H, W, k, s)
     part = torch.full((rows, 2, C), float("nan"), device=DEV)
-    K.dw_bwd_data(g[..., co:], draw[..., co:], eraw[..., co:], ge[..., co:], tap_major(w), ca[co:],
-                  cb[co:], cc[co:], es[co:], eh[co:], em[co:], er[co:], part, act, B, H, W, C, k, s,
+    K.dw_bwd_data(ddf[..., co:], draw[..., co:], eraw[..., co:], ge[..., co:], tap_major(w), None,
+                  None, None, es[co:], eh[co:], em[co:], er[co:], part, act, B, H, W, C, k, s,
                   ldg=Ct, ldd=Ct, lde=Ct, ldge=Ct)
     du = nhwc(torch.nn.grad.conv2d_input((B, C, H, W), w, nchw(dd), s, (k - 1) // 2, 1, C))
     ref = du * act_grad(pre, act)
@@ -122,9 +129,11 @@ def test_dw_backward(B, H, W, Ct, co, C, k, s):
     wrows = K.dw_bwd_weight_rows(B, C, H, W, k, s)
     wpart = torch.full((wrows, k * k, C), float("nan"), device=DEV)
     dw = torch.zeros(C, 1, k, k, device=DEV)
-    K.dw_bwd_weight(g[..., co:], draw[..., co:], eraw[..., co:], ca[co:], cb[co:], cc[co:], es[co:],
+    K.dw_bwd_weight(ddf[..., co:], draw[..., co:], eraw[..., co:], None, None, None, es[co:],
                     eh[co:], act, wpart, dw, B, H, W, C, k, s, ldg=Ct, ldd=Ct, lde=Ct)
-    wref = torch.nn.grad.conv2d_weight(nchw(u), (C, 1, k, k), nchw(dd), s, (k - 1) // 2, 1, C)
+    # the kernel applies BN + activation in fp32 on load (no bf16 rounding of the operand)
+    uf = act_f(pre, act)
+    wref = torch.nn.grad.conv2d_weight(nchw(uf), (C, 1, k, k), nchw(dd), s, (k - 1) // 2, 1, C)
     assert (dw - wref).abs().max().item() <= 2e-3 * wref.abs().max().item() + 1e-3
 
 
@@ -305,7 +314,7 @@ def test_refresh_and_gather_bit_exact():
 
 
 # ------------------------------------------------------------------------------------------------
-# materialised operands: the TMA-staged row-streaming kernels (dw_stream.cu), both strides
+# materialised operands (scale == NULL): same row-streaming kernels (dw2.cu / dw_stream.cu), both strides
 # ------------------------------------------------------------------------------------------------
 DW_REAL = [   # the AtomNAS-C layer shapes (4 / 2 / 1 columns per thread, 7 column-group warps)
     (3, 56, 56, 144, 0, 144, 7, 1), (2, 28, 28, 200, 8, 136, 5, 1), (3, 14, 14, 480, 0, 480, 7, 1),
