@@ -163,7 +163,7 @@ __device__ __forceinline__ void write_stats(const Params& p, float* red, int war
 // S*o + P, i.e. nch*U >= S*(Ho-1) + P + 1 rows are walked, the last P of them (beyond the image)
 // only finish and store rows.
 // ------------------------------------------------------------------------------------------------
-template <int K, int S, int MODE, int TC, int XF, int MB>
+template <int K, int S, int MODE, int TC, int XF, int MB, bool RAGGED>
 __global__ void __launch_bounds__(kThreads, MB) dw2_conv(const __grid_constant__ Params p) {
   extern __shared__ __align__(128) uint8_t dsm[];
   using G = Geom<K, S, TC>;
@@ -171,9 +171,11 @@ __global__ void __launch_bounds__(kThreads, MB) dw2_conv(const __grid_constant__
   constexpr bool EBN = MODE != 0, SWISH = MODE == 2;
   const int ncomp = p.nwc, D = p.depth, PW = p.PW;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t stage_bytes = static_cast<uint32_t>(U * PW * 128);
+  const uint32_t in_bytes = static_cast<uint32_t>(U * PW * 128);
+  const uint32_t e_bytes = EBN ? static_cast<uint32_t>(U * TC * p.nwc * 128) : 0u;   // U rows of eraw under the strip
+  const uint32_t stage_bytes = in_bytes + e_bytes;
   uint64_t *full, *empty;
-  ring_setup(dsm, D, stage_bytes, full, empty, ncomp, &p.tm_in, nullptr);
+  ring_setup(dsm, D, stage_bytes, full, empty, ncomp, &p.tm_in, EBN ? &p.tm_dd : nullptr);
   float* red = reinterpret_cast<float*>(empty + D);                     // [ncomp][2][64]
   const int cb0 = blockIdx.y * 64;
   const int ox0 = blockIdx.x * TC * p.nwc;
@@ -189,7 +191,10 @@ __global__ void __launch_bounds__(kThreads, MB) dw2_conv(const __grid_constant__
           const int st = it % D;
           mbar_wait(&empty[st], ((it / D) & 1) ^ 1);
           mbar_expect_tx(&full[st], stage_bytes);
-          tma_load_4d(dsm + (size_t)st * stage_bytes, &p.tm_in, &full[st], cb0, S * ox0 - P, c * U, n0 + gi);
+          uint8_t* sp = dsm + (size_t)st * stage_bytes;
+          tma_load_4d(sp, &p.tm_in, &full[st], cb0, S * ox0 - P, c * U, n0 + gi);
+          if (EBN)       // output rows c*U-P .. c*U+U-1-P finish in this stage: their eraw rows
+            tma_load_4d(sp + in_bytes, &p.tm_dd, &full[st], cb0, ox0, c * U - P, n0 + gi);
         }
     }
     return;
@@ -237,31 +242,36 @@ __global__ void __launch_bounds__(kThreads, MB) dw2_conv(const __grid_constant__
     for (int j = 0; j < TC; ++j) acc[s][j] = make_float2(0.f, 0.f);
 
   const int oxw = ox0 + TC * warp;                                      // first output column of the warp
-  const int ncols = min(TC, p.Wo - oxw);
-  // input columns S*oxw - P + cc, cc < NX: which of them lie inside the image (on-load transform
-  // must keep the zero padding zero)
+  const int ncols = RAGGED ? min(TC, p.Wo - oxw) : TC;
+  // XF 2 (identity / ReLU6 / Swish on load): input columns outside the image must stay zero after the
+  // affine transform -> per-column validity bits.  XF 1 (ReLU) needs none: the tensor map fills
+  // out-of-image elements with NaN and max(NaN, 0) = 0.
   uint32_t cmask = 0;
+  if (XF == 2) {
 #pragma unroll
-  for (int cc = 0; cc < NX; ++cc) {
-    const int col = S * oxw - P + cc;
-    if (col >= 0 && col < p.W) cmask |= 1u << cc;
+    for (int cc = 0; cc < NX; ++cc) {
+      const int col = S * oxw - P + cc;
+      if (col >= 0 && col < p.W) cmask |= 1u << cc;
+    }
   }
-  const bool edge = cmask != ((1u << NX) - 1u);
+  const bool edge = XF == 2 && cmask != ((1u << NX) - 1u);
   const bool live = (oxw < p.Wo) && ch_ok;
   const uint32_t* pbase = reinterpret_cast<const uint32_t*>(dsm) + (S * TC * warp) * 32 + lane;
+  const uint32_t* ebase = reinterpret_cast<const uint32_t*>(dsm + in_bytes) + (TC * warp) * 32 + lane;
   const int rowstride = PW * 32;                                        // words
-  const long long orow = (long long)p.Wo * p.ldo;                       // elements per output row
-  const long long erow = (long long)p.Wo * p.lde;
+  const int erowstride = TC * p.nwc * 32;
+  const long long ldo2 = p.ldo * 2;                                     // bytes between output columns
+  const long long orow2 = (long long)p.Wo * ldo2;                       // bytes per output row
   uint32_t it = 0;
   for (int gi = 0; gi < nimg; ++gi) {
     const int n = n0 + gi;
-    __nv_bfloat16* op = p.out + ((long long)n * p.Ho * p.Wo + oxw) * p.ldo + ch;       // output row 0
-    const __nv_bfloat16* ep = EBN ? p.eraw + ((long long)n * p.Ho * p.Wo + oxw) * p.lde + ch : nullptr;
+    char* op = reinterpret_cast<char*>(p.out + ((long long)n * p.Ho * p.Wo + oxw) * p.ldo + ch);   // output row 0
     for (int c = 0; c < p.nch; ++c, ++it) {
       const int st = it % D;
       mbar_wait(&full[st], (it / D) & 1);
       if (live) {
         const uint32_t* prow = pbase + (size_t)st * (stage_bytes / 4);
+        const uint32_t* erow = ebase + (size_t)st * (stage_bytes / 4);
         uint32_t xr[NX];
 #pragma unroll
         for (int cc = 0; cc < NX; ++cc) xr[cc] = prow[cc * 32];
@@ -272,8 +282,9 @@ __global__ void __launch_bounds__(kThreads, MB) dw2_conv(const __grid_constant__
 #pragma unroll
           for (int cc = 0; cc < NX; ++cc) x[cc] = unpack2(xr[cc]);
           if (u + 1 < U) {                                  // software pipeline: next row's words
+            prow += rowstride;
 #pragma unroll
-            for (int cc = 0; cc < NX; ++cc) xr[cc] = prow[(u + 1) * rowstride + cc * 32];
+            for (int cc = 0; cc < NX; ++cc) xr[cc] = prow[cc * 32];
           }
           // output row finished by this input row (static in u): S*o + P == r
           const bool completes = cmod(u - P, S) == 0;
@@ -283,16 +294,15 @@ __global__ void __launch_bounds__(kThreads, MB) dw2_conv(const __grid_constant__
           uint32_t xraw[TC];
 #pragma unroll
           for (int j = 0; j < TC; ++j) xraw[j] = 0u;
-          if (EBN && e_bn && emit) {                        // producer raw output under the finishing row
+          if (EBN && emit) {                                // row u of the stage's eraw box
 #pragma unroll
-            for (int j = 0; j < TC; ++j)
-              if (j < ncols) xraw[j] = __ldg(reinterpret_cast<const unsigned int*>(ep + j * p.lde));
+            for (int j = 0; j < TC; ++j) xraw[j] = erow[u * erowstride + j * 32];
           }
           if (r < p.H) {                                    // real image row (warp-uniform)
             if (XF != 0) {
 #pragma unroll
               for (int cc = 0; cc < NX; ++cc) x[cc] = xform<XF>(x[cc], xs, xh, xlo, xhi, xswish);
-              if (edge) {
+              if (XF == 2 && edge) {
 #pragma unroll
                 for (int cc = 0; cc < NX; ++cc)
                   if (!((cmask >> cc) & 1u)) x[cc] = make_float2(0.f, 0.f);
@@ -315,8 +325,8 @@ __global__ void __launch_bounds__(kThreads, MB) dw2_conv(const __grid_constant__
             if (emit) {
 #pragma unroll
               for (int j = 0; j < TC; ++j) {
-                float2 v = acc[slot][j];
-                if (j < ncols) {
+                if (!RAGGED || j < ncols) {
+                  float2 v = acc[slot][j];
                   float2 xe = make_float2(0.f, 0.f);
                   if (EBN) {
                     xe = unpack2(xraw[j]);
@@ -326,11 +336,10 @@ __global__ void __launch_bounds__(kThreads, MB) dw2_conv(const __grid_constant__
                   const float2 vr = unpack2(pk);
                   st1 = add2(st1, vr);
                   st2 = fma2(vr, EBN ? fma2(xe, er, emr) : vr, st2);
-                  *reinterpret_cast<uint32_t*>(op + j * p.ldo) = pk;
+                  *reinterpret_cast<uint32_t*>(op + j * ldo2) = pk;
                 }
               }
-              op += orow;
-              if (EBN) ep += erow;
+              op += orow2;
             }
 #pragma unroll
             for (int j = 0; j < TC; ++j) acc[slot][j] = make_float2(0.f, 0.f);
@@ -356,7 +365,7 @@ __global__ void __launch_bounds__(kThreads, MB) dw2_conv(const __grid_constant__
 // rows when r + P is a multiple of S (rows of dd beyond the image are zero-filled by TMA).
 // ------------------------------------------------------------------------------------------------
 template <int K, int S, int TC, int XF>
-__global__ void __launch_bounds__(kThreads, (K == 3 && TC == 4) ? 2 : 1) dw2_wgrad(const __grid_constant__ Params p) {
+__global__ void __launch_bounds__(kThreads, ((K == 3 || K == 5) && TC == 4) ? 2 : 1) dw2_wgrad(const __grid_constant__ Params p) {
   extern __shared__ __align__(128) uint8_t dsm[];
   using G = Geom<K, S, TC>;
   constexpr int P = G::P, U = G::U, R = G::R, NX = G::NX;
@@ -426,13 +435,15 @@ __global__ void __launch_bounds__(kThreads, (K == 3 && TC == 4) ? 2 : 1) dw2_wgr
 #pragma unroll
     for (int j = 0; j < TC; ++j) dr[s][j] = make_float2(0.f, 0.f);
   const int oxw = ox0 + TC * warp;
-  uint32_t cmask = 0;
+  uint32_t cmask = 0;                      // XF 1 (ReLU): NaN-filled padding, no mask (see dw2_conv)
+  if (XF == 2) {
 #pragma unroll
-  for (int cc = 0; cc < NX; ++cc) {
-    const int col = S * oxw - P + cc;
-    if (col >= 0 && col < p.W) cmask |= 1u << cc;
+    for (int cc = 0; cc < NX; ++cc) {
+      const int col = S * oxw - P + cc;
+      if (col >= 0 && col < p.W) cmask |= 1u << cc;
+    }
   }
-  const bool edge = cmask != ((1u << NX) - 1u);
+  const bool edge = XF == 2 && cmask != ((1u << NX) - 1u);
   const bool live = (oxw < p.Wo) && ch_ok;
   const uint32_t* ubase = reinterpret_cast<const uint32_t*>(dsm) + (S * TC * warp) * 32 + lane;
   const uint32_t* dbase = reinterpret_cast<const uint32_t*>(dsm + u_bytes) + (TC * warp) * 32 + lane;
@@ -466,7 +477,7 @@ __global__ void __launch_bounds__(kThreads, (K == 3 && TC == 4) ? 2 : 1) dw2_wgr
             if (XF != 0) {
 #pragma unroll
               for (int cc = 0; cc < NX; ++cc) x[cc] = xform<XF>(x[cc], xs, xh, xlo, xhi, xswish);
-              if (edge) {
+              if (XF == 2 && edge) {
 #pragma unroll
                 for (int cc = 0; cc < NX; ++cc)
                   if (!((cmask >> cc) & 1u)) x[cc] = make_float2(0.f, 0.f);
@@ -520,6 +531,7 @@ __global__ void __launch_bounds__(kThreads, (K == 3 && TC == 4) ? 2 : 1) dw2_wgr
 // ------------------------------------------------------------------------------------------------
 struct Cfg {
   int tc, nwc, strips, ipb, gz, nch, PW, depth, threads, parts, minb;
+  bool ragged;
   size_t smem;
 };
 
@@ -533,7 +545,8 @@ static bool low_occupancy() {
   return v;
 }
 
-// kind 0: forward / stride-1 data gradient (Ht x Wt = output size), 1: weight gradient (dd size).
+// kind 0: forward (Ht x Wt = output size), 3: stride-1 data gradient (+ eraw rows per stage),
+// 1: weight gradient (dd size).
 // 7 column-group warps of TC columns each cover the widths of every valid AtomNAS feature map
 // (112/56/28: 4 columns per thread, 14: 2, 7: 1) without idle threads; other widths take 4 (or 2)
 // columns per thread with a ragged last group.
@@ -546,6 +559,7 @@ static Cfg make_cfg(int kind, int B, int C, int Ht, int Wt, int Hin, int k, int 
   else { c.tc = 4; c.nwc = (Wt + 3) / 4; if (c.nwc > 7) c.nwc = 7; }
   const int TW = c.tc * c.nwc;
   c.strips = (Wt + TW - 1) / TW;
+  c.ragged = (Wt % TW) != 0;
   const int cblocks = (C + 63) / 64;
   const int P = (k - 1) / 2;
   const int U = (S == 1) ? k : k + 1, R = (S == 1) ? k : (k + 1) / 2;
@@ -555,10 +569,11 @@ static Cfg make_cfg(int kind, int B, int C, int Ht, int Wt, int Hin, int k, int 
   if (kind == 1) {
     stage += (size_t)R * TW * 128;
     rows = Hin + P;                                    // u rows -P .. Hin-1
-    c.minb = (k == 3 && c.tc == 4) ? 2 : 1;
+    c.minb = ((k == 3 || k == 5) && c.tc == 4) ? 2 : 1;
   } else {
     rows = S * (Ht - 1) + P + 1;                       // input rows 0 .. S*(Ho-1)+P
-    c.minb = (low_occupancy() || c.tc != 4) ? 1 : min_blocks(k);
+    if (kind == 3) stage += (size_t)U * TW * 128;      // producer raw output rows under the strip
+    c.minb = (low_occupancy() || c.tc != 4 || c.ragged) ? 1 : min_blocks(k);
   }
   c.nch = (rows + U - 1) / U;
   const size_t budget = (size_t)(200 * 1024) / c.minb - 4096;
@@ -611,21 +626,29 @@ static void fill(Params& p, const Cfg& c, int B, int C) {
 }
 
 template <int K, int S, int MODE, int XF>
-static Kernel conv_kernel(int tc) {
+static Kernel conv_kernel(int tc, bool ragged) {
+  if (ragged) {                      // widths that are not a multiple of the strip: guarded stores
+    switch (tc) {
+      case 4: return dw2_conv<K, S, MODE, 4, XF, 1, true>;
+      case 2: return dw2_conv<K, S, MODE, 2, XF, 1, true>;
+      case 1: return dw2_conv<K, S, MODE, 1, XF, 1, true>;
+    }
+    return nullptr;
+  }
   switch (tc) {
-    case 4: return low_occupancy() ? dw2_conv<K, S, MODE, 4, XF, 1> : dw2_conv<K, S, MODE, 4, XF, min_blocks(K)>;
-    case 2: return dw2_conv<K, S, MODE, 2, XF, 1>;
-    case 1: return dw2_conv<K, S, MODE, 1, XF, 1>;
+    case 4: return low_occupancy() ? dw2_conv<K, S, MODE, 4, XF, 1, false> : dw2_conv<K, S, MODE, 4, XF, min_blocks(K), false>;
+    case 2: return dw2_conv<K, S, MODE, 2, XF, 1, false>;
+    case 1: return dw2_conv<K, S, MODE, 1, XF, 1, false>;
   }
   return nullptr;
 }
 template <int K, int S, int MODE>
-static Kernel conv_kernel_xf(int tc, int xf) {
-  if (MODE != 0) return conv_kernel<K, S, MODE, 0>(tc);
+static Kernel conv_kernel_xf(int tc, int xf, bool ragged) {
+  if (MODE != 0) return conv_kernel<K, S, MODE, 0>(tc, ragged);
   switch (xf) {
-    case 0: return conv_kernel<K, S, 0, 0>(tc);
-    case 1: return conv_kernel<K, S, 0, 1>(tc);
-    default: return conv_kernel<K, S, 0, 2>(tc);
+    case 0: return conv_kernel<K, S, 0, 0>(tc, ragged);
+    case 1: return conv_kernel<K, S, 0, 1>(tc, ragged);
+    default: return conv_kernel<K, S, 0, 2>(tc, ragged);
   }
 }
 template <int K, int S, int XF>
@@ -658,31 +681,33 @@ static int fwd(const an_dw_fwd_args* a, cudaStream_t st) {
   Params p;
   memset(&p, 0, sizeof(p));
   const int U = (S == 1) ? a->k : a->k + 1;
-  if (int e = make_tmap_bf16_nhwc(&p.tm_in, a->x, a->C, a->W, a->H, a->B, a->ldx, 64, c.PW, U, 1)) return e;
+  const int xf = xf_mode(a->scale, a->act);
+  // ReLU on load: out-of-image elements are NaN-filled and become 0 through max(., 0)
+  if (int e = make_tmap_bf16_nhwc(&p.tm_in, a->x, a->C, a->W, a->H, a->B, a->ldx, 64, c.PW, U, 1, xf == 1)) return e;
   fill(p, c, a->B, a->C);
   p.w = a->w;
   p.out = reinterpret_cast<__nv_bfloat16*>(a->y); p.ldo = a->ldy;
   p.x_scale = a->scale; p.x_shift = a->shift;
   p.stats_part = a->stats_part; p.act = a->act;
   p.H = a->H; p.W = a->W; p.Ho = Ho; p.Wo = Wo;
-  const int xf = xf_mode(a->scale, a->act);
   Kernel kn = nullptr;
   switch (a->k * 10 + S) {
-    case 31: kn = conv_kernel_xf<3, 1, 0>(c.tc, xf); break;
-    case 51: kn = conv_kernel_xf<5, 1, 0>(c.tc, xf); break;
-    case 71: kn = conv_kernel_xf<7, 1, 0>(c.tc, xf); break;
-    case 32: kn = conv_kernel_xf<3, 2, 0>(c.tc, xf); break;
-    case 52: kn = conv_kernel_xf<5, 2, 0>(c.tc, xf); break;
-    case 72: kn = conv_kernel_xf<7, 2, 0>(c.tc, xf); break;
+    case 31: kn = conv_kernel_xf<3, 1, 0>(c.tc, xf, c.ragged); break;
+    case 51: kn = conv_kernel_xf<5, 1, 0>(c.tc, xf, c.ragged); break;
+    case 71: kn = conv_kernel_xf<7, 1, 0>(c.tc, xf, c.ragged); break;
+    case 32: kn = conv_kernel_xf<3, 2, 0>(c.tc, xf, c.ragged); break;
+    case 52: kn = conv_kernel_xf<5, 2, 0>(c.tc, xf, c.ragged); break;
+    case 72: kn = conv_kernel_xf<7, 2, 0>(c.tc, xf, c.ragged); break;
   }
   return launch(kn, p, c, st);
 }
 
 static int bwd_data1(const an_dw_bwd_args* a, cudaStream_t st) {      // stride 1: output size == dd size
-  const Cfg c = make_cfg(0, a->B, a->C, a->H, a->W, a->H, a->k, 1);
+  const Cfg c = make_cfg(3, a->B, a->C, a->H, a->W, a->H, a->k, 1);
   Params p;
   memset(&p, 0, sizeof(p));
   if (int e = make_tmap_bf16_nhwc(&p.tm_in, a->g, a->C, a->W, a->H, a->B, a->ldg, 64, c.PW, a->k, 1)) return e;
+  if (int e = make_tmap_bf16_nhwc(&p.tm_dd, a->eraw, a->C, a->W, a->H, a->B, a->lde, 64, c.tc * c.nwc, a->k, 1)) return e;
   fill(p, c, a->B, a->C);
   p.w = a->w;
   p.out = reinterpret_cast<__nv_bfloat16*>(a->ge); p.ldo = a->ldge;
@@ -693,9 +718,9 @@ static int bwd_data1(const an_dw_bwd_args* a, cudaStream_t st) {      // stride 
   const bool sw = a->e_scale != nullptr && a->act == ACT_SWISH;
   Kernel kn = nullptr;
   switch (a->k) {
-    case 3: kn = sw ? conv_kernel<3, 1, 2, 0>(c.tc) : conv_kernel<3, 1, 1, 0>(c.tc); break;
-    case 5: kn = sw ? conv_kernel<5, 1, 2, 0>(c.tc) : conv_kernel<5, 1, 1, 0>(c.tc); break;
-    case 7: kn = sw ? conv_kernel<7, 1, 2, 0>(c.tc) : conv_kernel<7, 1, 1, 0>(c.tc); break;
+    case 3: kn = sw ? conv_kernel<3, 1, 2, 0>(c.tc, c.ragged) : conv_kernel<3, 1, 1, 0>(c.tc, c.ragged); break;
+    case 5: kn = sw ? conv_kernel<5, 1, 2, 0>(c.tc, c.ragged) : conv_kernel<5, 1, 1, 0>(c.tc, c.ragged); break;
+    case 7: kn = sw ? conv_kernel<7, 1, 2, 0>(c.tc, c.ragged) : conv_kernel<7, 1, 1, 0>(c.tc, c.ragged); break;
   }
   return launch(kn, p, c, st);
 }
@@ -707,13 +732,13 @@ static int wgrad(const an_dw_bwd_args* a, float* partials, cudaStream_t st) {
   Params p;
   memset(&p, 0, sizeof(p));
   const int U = (S == 1) ? a->k : a->k + 1, R = (S == 1) ? a->k : (a->k + 1) / 2;
-  if (int e = make_tmap_bf16_nhwc(&p.tm_in, a->eraw, a->C, a->W, a->H, a->B, a->lde, 64, c.PW, U, 1)) return e;
+  const int xf = xf_mode(a->e_scale, a->act);
+  if (int e = make_tmap_bf16_nhwc(&p.tm_in, a->eraw, a->C, a->W, a->H, a->B, a->lde, 64, c.PW, U, 1, xf == 1)) return e;
   if (int e = make_tmap_bf16_nhwc(&p.tm_dd, a->g, a->C, Wo, Ho, a->B, a->ldg, 64, c.tc * c.nwc, R, 1)) return e;
   fill(p, c, a->B, a->C);
   p.wpart = partials;
   p.x_scale = a->e_scale; p.x_shift = a->e_shift; p.act = a->act;
   p.H = a->H; p.W = a->W; p.Ho = Ho; p.Wo = Wo;
-  const int xf = xf_mode(a->e_scale, a->act);
   Kernel kn = nullptr;
   switch (a->k * 10 + S) {
     case 31: kn = wgrad_kernel_xf<3, 1>(c.tc, xf); break;
@@ -775,7 +800,7 @@ extern "C" int an_dw_fwd(const an_dw_fwd_args* a, void* stream) {
 
 extern "C" int an_dw_bwd_data_stats_rows(int B, int C, int H, int W, int k, int stride, int /*fused*/) {
   if (stride == 2) return dw_stream_dgrad2_rows(B, C, H, W, k);
-  return dw2::make_cfg(0, B, C, H, W, H, k, 1).parts;
+  return dw2::make_cfg(3, B, C, H, W, H, k, 1).parts;
 }
 
 extern "C" int an_dw_bwd_data(const an_dw_bwd_args* a, void* stream) {

@@ -58,6 +58,7 @@ class BNGroup(object):
         self.eps = members[0][0].eps
         self.momentum = members[0][0].momentum
         self.count = 0.0                            # elements per channel of the last forward
+        self.split = None                           # one BatchNorm scattered over padded slots (fused block)
 
 
 class BlockPlan(object):
@@ -89,6 +90,9 @@ class Engine(object):
         self.buf_slots = []         # (module, attr, offset, numel)
         self.bn_groups = []
         self.refresh = []           # [src_ld, src_off, dst_off, rows, cols, dst_ld, transpose, dst_f32]
+        # fused blocks: ONE BatchNorm / conv parameter serves several 8-padded branch slots; the
+        # kernels work on padded shadow vectors and these (src, dst, n) segments keep them in sync
+        self.seg_in_P, self.seg_in_S, self.seg_out_S, self.seg_out_G = [], [], [], []
         self.modules = set()
         if self.is_net:
             feats = list(root.features.children())
@@ -131,6 +135,31 @@ class Engine(object):
         self.bn_groups.append(g)
         return g
 
+    def _bn_group_split(self, bn, pieces, C):
+        """One nn.BatchNorm2d whose channels [start, start+width) sit in padded slot `off` (pieces =
+        [(start, width, off)], C = padded width).  The module's parameters / running statistics stay
+        contiguous in the master arenas (state_dict, optimizer, EMA see them unchanged); the kernels
+        use padded shadow vectors in the same arenas, synchronised by segment copies."""
+        g = BNGroup([(bn, 0)])
+        g.C, g.split = C, pieces
+        n = bn.num_features
+        m_g, m_b = self.pa.add(n), self.pa.add(n)
+        m_rm, m_rv = self.sa.add(n), self.sa.add(n)
+        self.param_slots.append((bn.weight, m_g, n, 0.0, 0.0))
+        self.param_slots.append((bn.bias, m_b, n, 0.0, 0.0))
+        self.buf_slots.append((bn, "running_mean", m_rm, n))
+        self.buf_slots.append((bn, "running_var", m_rv, n))
+        g.g_off, g.b_off = self.pa.add(C), self.pa.add(C)          # shadows: frozen (wd_flag -1) pad space
+        g.rm_off, g.rv_off = self.sa.add(C), self.sa.add(C)
+        for start, width, off in pieces:
+            self.seg_in_P += [(m_g + start, g.g_off + off, width), (m_b + start, g.b_off + off, width)]
+            self.seg_in_S += [(m_rm + start, g.rm_off + off, width), (m_rv + start, g.rv_off + off, width)]
+            self.seg_out_S += [(g.rm_off + off, m_rm + start, width), (g.rv_off + off, m_rv + start, width)]
+            self.seg_out_G += [(g.g_off + off, m_g + start, width), (g.b_off + off, m_b + start, width)]
+        g.v_off = self.va.add(7 * g.C)
+        self.bn_groups.append(g)
+        return g
+
     def _gemm_weight(self, rows, cols):
         """Reserve bf16 [rows, cols] and its transpose [cols, rows] (rows/cols already padded)."""
         return self.wa16.add(rows * cols), self.wa16.add(rows * cols)
@@ -147,9 +176,12 @@ class Engine(object):
         return s
 
     def _plan_block(self, b, name):
-        if type(b).__name__ == "InvertedResidualChannelsFused" or not isinstance(b, mb.InvertedResidualChannels):
+        if type(b).__name__ == "InvertedResidualChannelsFused" or hasattr(b, "depth_ops"):
+            return self._plan_block_fused(b, name)
+        if not isinstance(b, mb.InvertedResidualChannels):
             raise NotImplementedError("block type %s has no sm_100a path yet" % type(b).__name__)
         p = BlockPlan()
+        p.fused, p.se = False, None
         p.mod, p.name = b, name
         p.inp, p.oup, p.stride, p.expand = b.input_dim, b.output_dim, b.stride, b.expand
         if p.inp % 8 or p.oup % 8:
@@ -189,11 +221,80 @@ class Engine(object):
         p.bn_d = self._bn_group([br.dw_bn for br in p.branches])
         for br in p.branches:
             br.wp_off = self._slot(br.proj.weight, 1.0)
+            br.wp_ss = br.h                          # pitch of the projection weight [oup, h_i]
         p.wp16, p.wpT16 = self._gemm_weight(p.oup, p.Kh)
         for br in p.branches:
             self.refresh.append([br.h, br.wp_off, p.wp16 + br.off, p.oup, br.h, p.Kh, 0, 0])
             self.refresh.append([br.h, br.wp_off, p.wpT16 + br.off * p.oup, p.oup, br.h, p.oup, 1, 0])
         p.bn_p = self._bn_group([b.pw_bn])
+        return p
+
+    def _plan_block_fused(self, b, name):
+        """InvertedResidualChannelsFused (+ SqueezeAndExcitation), models/mobilenet_base.py:145-274.
+        Same launch plan as the branch block: the single expand conv / BN and the single projection
+        conv are addressed per branch through offsets into their (contiguous) master tensors."""
+        p = BlockPlan()
+        p.mod, p.name, p.fused = b, name, True
+        p.inp, p.oup, p.stride, p.expand = b.input_dim, b.output_dim, b.stride, b.expand
+        if p.inp % 8 or p.oup % 8:
+            raise NotImplementedError("block in/out widths must be multiples of 8 (round_nearest=8)")
+        p.res = b.use_res_connect
+        p.act = mb.active_fn_id(b.active_fn)
+        p.channels = list(b.channels)
+        p.branches, off, start = [], 0, 0
+        for op, h, k in zip(b.depth_ops, b.channels, b.kernel_sizes):
+            br = BlockPlan()
+            cbr = op[-1]                                     # Sequential([Narrow,] ConvBNReLU)
+            br.h, br.hp, br.off, br.k, br.start = h, _r8(h), off, k, start
+            br.dw_conv, br.dw_bn = cbr[0], cbr[1]
+            off += br.hp
+            start += h
+            p.branches.append(br)
+        p.Kh, total = off, start
+        if b.expand:
+            conv, bn = b.expand_conv[0], b.expand_conv[1]
+            base = self._slot(conv.weight, 1.0)
+            for br in p.branches:
+                br.we_off = base + br.start * p.inp
+            p.bn_e = self._bn_group_split(bn, [(br.start, br.h, br.off) for br in p.branches], p.Kh)
+            p.we16, p.weT16 = self._gemm_weight(p.Kh, p.inp)
+            for br in p.branches:
+                self.refresh.append([p.inp, br.we_off, p.we16 + br.off * p.inp, br.h, p.inp, p.inp, 0, 0])
+                self.refresh.append([p.inp, br.we_off, p.weT16 + br.off, br.h, p.inp, p.Kh, 1, 0])
+        elif p.Kh != p.inp:
+            raise NotImplementedError("non-expanding block with padded width")
+        for br in p.branches:
+            br.wd_off = self._slot(br.dw_conv.weight, 1.0)
+            br.wd32 = self.wa32.add(br.k * br.k * br.hp)
+            self.refresh.append([br.k * br.k, br.wd_off, br.wd32, br.h, br.k * br.k, br.hp, 1, 1])
+        p.bn_d = self._bn_group([br.dw_bn for br in p.branches])
+        proj, pbn = b.project_conv[0], b.project_conv[1]
+        base = self._slot(proj.weight, 1.0)                  # [oup, total]
+        for br in p.branches:
+            br.wp_off, br.wp_ss = base + br.start, total
+        p.wp16, p.wpT16 = self._gemm_weight(p.oup, p.Kh)
+        for br in p.branches:
+            self.refresh.append([total, br.wp_off, p.wp16 + br.off, p.oup, br.h, p.Kh, 0, 0])
+            self.refresh.append([total, br.wp_off, p.wpT16 + br.off * p.oup, p.oup, br.h, p.oup, 1, 0])
+        p.bn_p = self._bn_group([pbn])
+        p.se = None
+        se = b.se_op
+        if hasattr(se, "se_reduce"):
+            q = BlockPlan()
+            q.total, q.mid = total, se.n_hidden
+            q.act = _act_of(se.active_fn)
+            q.w1 = self._slot(se.se_reduce.weight, 1.0)       # [mid, total, 1, 1]
+            q.b1 = self._slot(se.se_reduce.bias, 0.0)         # 1-D non-classifier: no L2 (optim.py:239-240)
+            q.w2 = self._slot(se.se_expand.weight, 1.0)       # [total, mid, 1, 1]
+            q.b2 = self._slot(se.se_expand.bias, 0.0)
+            chmap = [-1] * p.Kh
+            inv = [0] * total
+            for br in p.branches:
+                for i in range(br.h):
+                    chmap[br.off + i] = br.start + i
+                    inv[br.start + i] = br.off + i
+            q.chmap_host, q.inv_host = chmap, inv
+            p.se = q
         return p
 
     def _plan_head(self, m, classifier):
@@ -259,6 +360,21 @@ class Engine(object):
         self.weights_version = -1
         self.grad_views = None
 
+        def seg_table(segs):
+            rows, tl = [], 0
+            for src, dst, n in segs:
+                rows.append([n, src, dst, 1, n, n, 0, 1, tl])
+                tl += (n + 31) // 32
+            return (torch.tensor(rows, dtype=torch.int64, device=dev), len(rows), tl) if rows else None
+
+        self.tab_in_P, self.tab_in_S = seg_table(self.seg_in_P), seg_table(self.seg_in_S)
+        self.tab_out_S, self.tab_out_G = seg_table(self.seg_out_S), seg_table(self.seg_out_G)
+        self.has_split = self.tab_in_P is not None
+        for p in self.blocks:
+            if getattr(p, "se", None) is not None:
+                p.se.chmap = torch.tensor(p.se.chmap_host, dtype=torch.int32, device=dev)
+                p.se.inv_map = torch.tensor(p.se.inv_host, dtype=torch.int32, device=dev)
+
     # ---- small accessors ----------------------------------------------------------------------
     def _bnv(self, g, i):
         return self.V[g.v_off + i * g.C: g.v_off + (i + 1) * g.C]
@@ -289,6 +405,11 @@ class Engine(object):
         for name, pen in named_penalties:
             off, n = by_id[id(named_params[name])]
             self.l1_pen[off:off + n] = float(pen)
+
+    def _copy_segments(self, tab, arena):
+        """Table-driven fp32 segment copies inside one arena (master <-> padded shadow vectors)."""
+        if tab is not None:
+            K.refresh_weights(tab[0], tab[1], tab[2], arena, None, arena)
 
     def set_weight_decay_method(self, method):
         """Which elements take L2 (utils/optim.py:210-249).  'mnas': every conv / fc weight and the
@@ -330,7 +451,7 @@ class Engine(object):
         bf = _Buf()
         bf.B = B
         part_max, wpart_max = 8, 8
-        big_e, big_d, big_y = 8, 8, 8
+        big_e, big_d, big_y, se_max = 8, 8, 8, 0
 
         def bf16(*shape):
             return torch.empty(shape, device=dev, dtype=_BF16)
@@ -369,6 +490,14 @@ class Engine(object):
                         bb.e_raw.zero_()
                 bb.p_raw = bf16(Mo, p.oup)
                 big_d = max(big_d, Mo * p.Kh)
+                if p.se is not None:
+                    q = p.se
+                    bb.se_pool = torch.empty(B, p.Kh, device=dev)
+                    bb.se_h = torch.empty(B, q.mid, device=dev)
+                    bb.se_gate = torch.empty(B, p.Kh, device=dev)
+                    bb.vg = bf16(Mo, p.Kh)           # act(bn(d_raw)) * gate: the projection's A operand
+                    se_max = max(se_max, B * max(p.Kh, q.total))
+                    part_max = max(part_max, K.se_bwd_apply_rows(Mo, p.Kh) * 2 * p.Kh)
                 for br in p.branches:
                     part_max = max(part_max, K.dw_fwd_stats_rows(B, br.hp, ho, wo, br.k, p.stride, False) * 2 * br.hp,
                                    K.dw_bwd_data_stats_rows(B, br.hp, h, w, br.k, p.stride, False) * 2 * br.hp)
@@ -407,6 +536,8 @@ class Engine(object):
             bf.g_e = bf16(big_e)
             bf.dp = bf16(big_y)
             bf.dy = [bf16(big_y), bf16(big_y)]
+            if se_max:                               # SE backward scratch: dgate, dz, dh, ds
+                bf.se_scratch = [torch.empty(se_max, device=dev) for _ in range(4)]
         self.bufs = {key: bf}          # keep one shape resident (train and calibration alternate rarely)
         return bf
 
@@ -472,6 +603,9 @@ class Engine(object):
         self._fwd_gen += 1
         bf.training, bf.seed, bf.seed_dev = training, seed, seed_dev
         self._begin_bn_step(training)
+        if self.has_split:                           # master gamma / beta / running stats -> padded shadows
+            self._copy_segments(self.tab_in_P, self.P)
+            self._copy_segments(self.tab_in_S, self.S)
         part = bf.part
         stats = part if training else None
         if self.is_net:
@@ -492,6 +626,8 @@ class Engine(object):
             bf.x = cur
         for p, bb in zip(self.blocks, bf.blk):
             cur = self._block_fwd(p, bb, cur, B, training, stats, part)
+        if self.has_split and training:              # updated running statistics back to the modules' tensors
+            self._copy_segments(self.tab_out_S, self.S)
         if not self.is_net:
             return cur.view(B, bf.blk[-1].ho, bf.blk[-1].wo, -1)
         TAG[0] = "fwd.head"
@@ -530,9 +666,23 @@ class Engine(object):
                      shift=None if x_shift is None else x_shift[br.off:])
             self._bn_fwd(p.bn_d, part, K.dw_fwd_stats_rows(B, br.hp, bb.ho, bb.wo, br.k, p.stride, False), Mo,
                          training, C=br.hp, off=br.off)
-        TAG[0] = "fwd.project"
-        K.pw_gemm(bb.d_raw, self.W16[p.wp16:], bb.p_raw, Mo, p.oup, p.Kh, a_mode=1, a_act=p.act,
-                  a1=self.bn_vec(p.bn_d, "scale"), a3=self.bn_vec(p.bn_d, "shift"), stats_part=stats)
+        if p.se is not None:
+            # squeeze-and-excitation on the activated depthwise output (mobilenet_base.py:93-117):
+            # pooled mean -> two tiny FCs -> sigmoid gate -> vg = v * gate feeds the projection
+            TAG[0] = "fwd.se"
+            q = p.se
+            d_scale, d_shift = self.bn_vec(p.bn_d, "scale"), self.bn_vec(p.bn_d, "shift")
+            HW = Mo // B
+            K.se_pool(bb.d_raw, p.Kh, d_scale, d_shift, p.act, B, HW, p.Kh, bb.se_pool)
+            K.se_gate(bb.se_pool, self.P[q.w1:], self.P[q.b1:], self.P[q.w2:], self.P[q.b2:], q.chmap, q.act, B,
+                      p.Kh, q.total, q.mid, bb.se_h, bb.se_gate)
+            K.se_scale(bb.d_raw, p.Kh, d_scale, d_shift, p.act, bb.se_gate, B, HW, p.Kh, bb.vg, p.Kh)
+            TAG[0] = "fwd.project"
+            K.pw_gemm(bb.vg, self.W16[p.wp16:], bb.p_raw, Mo, p.oup, p.Kh, stats_part=stats)
+        else:
+            TAG[0] = "fwd.project"
+            K.pw_gemm(bb.d_raw, self.W16[p.wp16:], bb.p_raw, Mo, p.oup, p.Kh, a_mode=1, a_act=p.act,
+                      a1=self.bn_vec(p.bn_d, "scale"), a3=self.bn_vec(p.bn_d, "shift"), stats_part=stats)
         self._bn_fwd(p.bn_p, part, K.pw_gemm_stats_rows(Mo, p.oup), Mo, training)
         K.affine_act(bb.p_raw, bb.y, Mo, p.oup, ld1=p.oup, ldo=p.oup, x2=x if p.res else None, ld2=p.inp,
                      a1=self.bn_vec(p.bn_p, "scale"), a3=self.bn_vec(p.bn_p, "shift"))
@@ -550,6 +700,9 @@ class Engine(object):
         B = bf.B
         part, wpart = bf.part, bf.wpart
         G, P = self.G, self.P
+        final_ready = grad_ready
+        if self.has_split:                           # shadow -> master gradient copies happen at the very end
+            grad_ready = None
         if self.is_net:
             TAG[0] = "bwd.head"
             hd = self.head
@@ -587,6 +740,7 @@ class Engine(object):
                 grad_ready(self._block_first_offset(p))
             dy, slot = dx, 1 - slot
         if not self.is_net:
+            self._copy_segments(self.tab_out_G, self.G)
             b0 = bf.blk[0]
             return dy[:b0.M * self.blocks[0].inp].view(B, b0.hin, b0.win, -1)
         TAG[0] = "bwd.stem"
@@ -600,8 +754,9 @@ class Engine(object):
         self._bn_bwd(s.bn, part, K.col_reduce_rows(M0, s.C))
         K.stem_wgrad(bf.x, gs, bf.s_raw, self.bn_vec(s.bn, "ca"), self.bn_vec(s.bn, "cb"), self.bn_vec(s.bn, "cc"),
                      wpart, G[s.w_off:], B, bf.x.shape[2], bf.x.shape[3], s.C, ldg=s.C, lds=s.C)
-        if grad_ready is not None:
-            grad_ready(0)
+        self._copy_segments(self.tab_out_G, self.G)
+        if final_ready is not None:
+            final_ready(0)
         return None
 
     def _block_first_offset(self, p):
@@ -610,7 +765,7 @@ class Engine(object):
 
     def _block_bwd(self, p, bb, dy, dx, B, part, wpart, bf):
         """dy: grad wrt block output [Mo, oup]; writes grad wrt block input into dx [M, inp]."""
-        G = self.G
+        G, P = self.G, self.P
         M, Mo = bb.M, bb.Mo
         act = p.act
         # pw_bn backward: reductions over (dy, p_raw), then dp_raw = ca*dy + cb*p_raw + cc
@@ -622,18 +777,40 @@ class Engine(object):
         K.affine_act(dy, dp, Mo, p.oup, ld1=p.oup, ldo=p.oup, x2=bb.p_raw, ld2=p.oup,
                      a1=self.bn_vec(p.bn_p, "ca"), a2=self.bn_vec(p.bn_p, "cb"), a3=self.bn_vec(p.bn_p, "cc"))
         d_scale, d_shift = self.bn_vec(p.bn_d, "scale"), self.bn_vec(p.bn_d, "shift")
-        # project weight gradient: dWp[oup, h_i] = dp^T act(bn(d_raw))
-        TAG[0] = "bwd.project_wgrad"
-        sp = K.pw_wgrad(bb.d_raw, dp, wpart, Mo, p.Kh, p.oup, p_mode=1, p_act=act, a1=d_scale, a3=d_shift)
-        for br in p.branches:
-            K.wgrad_reduce(wpart, sp, p.Kh, p.oup, G[br.wp_off:], 1, br.h, row0=br.off, nrows=br.h)
-        # project data gradient with act/BN backward epilogue -> g_d
         g_d = bf.g_d
-        TAG[0] = "bwd.project_dgrad"
-        K.pw_gemm(dp, self.W16[p.wpT16:], g_d, Mo, p.Kh, p.oup, epi_mode=1, r=bb.d_raw, ldr=p.Kh,
-                  r_scale=d_scale, r_shift=d_shift, r_mean=self.bn_vec(p.bn_d, "mean"),
-                  r_rstd=self.bn_vec(p.bn_d, "rstd"), r_act=act, stats_part=part)
-        self._bn_bwd(p.bn_d, part, K.pw_gemm_stats_rows(Mo, p.Kh), raw_second=True)
+        if p.se is None:
+            # project weight gradient: dWp[oup, h_i] = dp^T act(bn(d_raw))
+            TAG[0] = "bwd.project_wgrad"
+            sp = K.pw_wgrad(bb.d_raw, dp, wpart, Mo, p.Kh, p.oup, p_mode=1, p_act=act, a1=d_scale, a3=d_shift)
+            for br in p.branches:
+                K.wgrad_reduce(wpart, sp, p.Kh, p.oup, G[br.wp_off:], 1, br.wp_ss, row0=br.off, nrows=br.h)
+            # project data gradient with act/BN backward epilogue -> g_d
+            TAG[0] = "bwd.project_dgrad"
+            K.pw_gemm(dp, self.W16[p.wpT16:], g_d, Mo, p.Kh, p.oup, epi_mode=1, r=bb.d_raw, ldr=p.Kh,
+                      r_scale=d_scale, r_shift=d_shift, r_mean=self.bn_vec(p.bn_d, "mean"),
+                      r_rstd=self.bn_vec(p.bn_d, "rstd"), r_act=act, stats_part=part)
+            self._bn_bwd(p.bn_d, part, K.pw_gemm_stats_rows(Mo, p.Kh), raw_second=True)
+        else:
+            # SE block: the projection saw vg = v * gate.  dWp = dp^T vg; D = dp Wp is materialised,
+            # the gate path is differentiated by the se_* kernels, and
+            # g_d = (D*gate + ds/HW) * act'(.) comes out of one fused element-wise pass with the
+            # BN-backward partials (mobilenet_base.py:93-117 under autograd)
+            q = p.se
+            HW = Mo // B
+            TAG[0] = "bwd.project_wgrad"
+            sp = K.pw_wgrad(bb.vg, dp, wpart, Mo, p.Kh, p.oup)
+            for br in p.branches:
+                K.wgrad_reduce(wpart, sp, p.Kh, p.oup, G[br.wp_off:], 1, br.wp_ss, row0=br.off, nrows=br.h)
+            TAG[0] = "bwd.project_dgrad"
+            K.pw_gemm(dp, self.W16[p.wpT16:], g_d, Mo, p.Kh, p.oup)
+            TAG[0] = "bwd.se"
+            dgate, dz, dh, ds = bf.se_scratch
+            K.se_pool(bb.d_raw, p.Kh, d_scale, d_shift, act, B, HW, p.Kh, dgate, D=g_d, ldD=p.Kh, mean=False)
+            K.se_gate_bwd(dgate, bb.se_gate, bb.se_h, bb.se_pool, P[q.w1:], P[q.w2:], q.chmap, q.inv_map, q.act, B,
+                          p.Kh, q.total, q.mid, dz, dh, ds, G[q.w1:], G[q.b1:], G[q.w2:], G[q.b2:])
+            K.se_bwd_apply(g_d, p.Kh, bb.d_raw, p.Kh, d_scale, d_shift, self.bn_vec(p.bn_d, "mean"),
+                           self.bn_vec(p.bn_d, "rstd"), act, bb.se_gate, ds, B, HW, p.Kh, g_d, p.Kh, part)
+            self._bn_bwd(p.bn_d, part, K.se_bwd_apply_rows(Mo, p.Kh))
         # dd = ca*g + cb*d_raw + cc (BN-backward apply), materialised in place: both depthwise
         # gradient kernels stage it with TMA and must not spend issue slots on the transform
         TAG[0] = "bwd.dd"
@@ -770,7 +947,9 @@ engine_of_tensor = engine_of_param
 
 def _still_valid(eng, root):
     for p in eng.blocks:
-        if list(p.mod.channels) != p.channels or (p.branches and p.branches[0].proj is not p.mod.ops[0][-1]):
+        if list(p.mod.channels) != p.channels:
+            return False
+        if not p.fused and p.branches and p.branches[0].proj is not p.mod.ops[0][-1]:
             return False
     return next(root.parameters()).device == eng.dev
 
@@ -837,7 +1016,7 @@ def run_module(module, x):
     if not x.is_cuda:
         raise RuntimeError("atomnas_b200: CPU tensor passed to the B200 hot path (no CPU fallback)")
     is_net = hasattr(module, "features") and hasattr(module, "classifier")
-    if not is_net and not isinstance(module, mb.InvertedResidualChannels):
+    if not is_net and not (isinstance(module, mb.InvertedResidualChannels) or hasattr(module, "depth_ops")):
         raise NotImplementedError("standalone %s forward is not part of the B200 hot path" % type(module).__name__)
     eng = get_engine(module)
     need_grad = torch.is_grad_enabled() and module.training and any(p.requires_grad for p in eng.params())
@@ -895,6 +1074,30 @@ def _fire_profiling_hooks(model, eng, x):
     conv_bn_act(feats[0], 3, eng.stem.C, H, W, h, w, B)
     for p in eng.blocks:
         ho, wo = ((h + 1) // 2, (w + 1) // 2) if p.stride == 2 else (h, w)
+        if p.fused:
+            m = p.mod
+            total = sum(br.h for br in p.branches)
+            if p.expand:
+                conv_bn_act(m.expand_conv, p.inp, total, h, w, h, w, B)
+            else:
+                fire(m.expand_conv, (B, p.inp, h, w), (B, p.inp, h, w))
+            for op, br in zip(m.depth_ops, p.branches):
+                if p.expand:
+                    fire(op[0], (B, total, h, w), (B, br.h, h, w))
+                conv_bn_act(op[-1], br.h, br.h, h, w, ho, wo, B)
+                fire(op, (B, total if p.expand else p.inp, h, w), (B, br.h, ho, wo))
+            fire(m.depth_ops, (B, total, h, w), (B, total, ho, wo))
+            if p.se is not None:
+                fire(m.se_op.se_reduce, (B, total, 1, 1), (B, p.se.mid, 1, 1))
+                fire(m.se_op.active_fn, (B, p.se.mid, 1, 1), (B, p.se.mid, 1, 1))
+                fire(m.se_op.se_expand, (B, p.se.mid, 1, 1), (B, total, 1, 1))
+            fire(m.se_op, (B, total, ho, wo), (B, total, ho, wo))
+            fire(m.project_conv[0], (B, total, ho, wo), (B, p.oup, ho, wo))
+            fire(m.project_conv[1], (B, p.oup, ho, wo), (B, p.oup, ho, wo))
+            fire(m.project_conv, (B, total, ho, wo), (B, p.oup, ho, wo))
+            fire(m, (B, p.inp, h, w), (B, p.oup, ho, wo))
+            h, w = ho, wo
+            continue
         for op, br in zip(p.mod.ops, p.branches):
             d = 0
             if p.expand:

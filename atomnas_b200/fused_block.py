@@ -2,9 +2,11 @@
 
 Mirrors models/mobilenet_base.py:93-117 (SE) and :145-274 (fused block): constructor arguments,
 child names (`expand_conv`, `depth_ops`, `project_conv`, `se_op`) and therefore state_dict keys,
-so AtomNAS-A+/B+/C+ checkpoints and YAMLs load.  The sm_100a execution path for this block type
-(SE gate fused into the projection GEMM's A-prologue, Swish everywhere) is the next row of the
-scope table and is NOT built yet: `forward` raises instead of silently running PyTorch eager.
+so AtomNAS-A+/B+/C+ checkpoints and YAMLs load.  Execution: `forward` hands the block (or the whole
+network it sits in) to engine.Engine, which maps the single expand conv / BatchNorm and the single
+projection conv onto the same branch-fused kernels as InvertedResidualChannels (8-padded channel
+slots per branch) and runs the SE gate with the kernels of csrc/se.cu.  There is no PyTorch / CPU
+fallback.  A stand-alone SqueezeAndExcitation call is not part of the hot path and raises.
 """
 import collections
 
@@ -24,7 +26,8 @@ class SqueezeAndExcitation(nn.Module):
         self.active_fn = active_fn()
 
     def forward(self, x):
-        raise NotImplementedError("SqueezeAndExcitation has no sm_100a kernel path yet (scope table 8f-1)")
+        raise NotImplementedError("stand-alone SqueezeAndExcitation is not on the B200 hot path: it runs inside "
+                                  "InvertedResidualChannelsFused (csrc/se.cu)")
 
     def __repr__(self):
         return "{}({}, {}, spatial_dims={}, active_fn={})".format(
@@ -79,8 +82,8 @@ class InvertedResidualChannelsFused(nn.Module):
         return list(self.get_named_depthwise_bn().values())
 
     def forward(self, x):
-        raise NotImplementedError("InvertedResidualChannelsFused has no sm_100a kernel path yet "
-                                  "(scope table 8f-1); use block='InvertedResidualChannels'")
+        from . import engine
+        return engine.run_module(self, x)
 
     def __repr__(self):
         return ("{}({}, {}, channels={}, kernel_sizes={}, expand={}, stride={}, se_ratio={})").format(

@@ -227,3 +227,9 @@ def _get_named_block_list(m):
     """features[1:-2] keyed by their state_dict prefix."""
     children = list(m.features.named_children())[1:-2]
     return collections.OrderedDict(("features.{}".format(n), b) for n, b in children)
+
+
+# the fused sibling and its SE module live in fused_block.py; exported here under the reference's
+# names (models.mobilenet_base.InvertedResidualChannelsFused / SqueezeAndExcitation are looked up
+# by utils/model_profiling.py:105-127 and models/searched_network.py:86-92)
+from .fused_block import InvertedResidualChannelsFused, SqueezeAndExcitation  # noqa: E402,F401

@@ -214,6 +214,31 @@ def profile_macs(model, input_size):
     for block in feats[1:-2]:
         ho = (h + 1) // 2 if block.stride == 2 else h
         block.n_macs = 0
+        if hasattr(block, "depth_ops"):                        # InvertedResidualChannelsFused (:121-130)
+            parts = []
+            if block.expand:
+                block.expand_conv[0].n_macs = conv_macs(block.expand_conv[0], h)
+                block.expand_conv.n_macs = block.expand_conv[0].n_macs
+                parts.append(block.expand_conv.n_macs)
+            for op in block.depth_ops:
+                conv = op[-1][0]
+                conv.n_macs = conv_macs(conv, ho)
+                op.n_macs = conv.n_macs
+                parts.append(op.n_macs)
+            proj = block.project_conv[0]
+            proj.n_macs = conv_macs(proj, ho)
+            block.project_conv.n_macs = proj.n_macs
+            parts.append(proj.n_macs)
+            se = block.se_op
+            if hasattr(se, "se_reduce"):
+                se.se_reduce.n_macs = conv_macs(se.se_reduce, 1)
+                se.se_expand.n_macs = conv_macs(se.se_expand, 1)
+                se.n_macs = se.n_feature * ho * ho + se.se_reduce.n_macs + se.se_expand.n_macs
+                parts.append(se.n_macs)
+            block.n_macs = sum(parts)
+            total += block.n_macs
+            h = ho
+            continue
         for op in block.ops:
             d = 1 if block.expand else 0
             convs = [(op[d][0], ho), (op[d + 1], ho)]          # depthwise, projection: output res

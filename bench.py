@@ -48,6 +48,16 @@ SEARCHED_C = [[[3], [32]], [[3, 5, 7], [15, 23, 13]], [[3, 5, 7], [20, 3, 2]], [
               [[3, 5, 7], [57, 40, 36]], [[3, 5, 7], [61, 34, 26]], [[3, 5, 7], [87, 38, 33]],
               [[3, 5, 7], [454, 468, 468]], [[3, 5, 7], [188, 137, 306]], [[3, 5, 7], [253, 187, 314]],
               [[3, 5, 7], [345, 202, 233]], [[3, 5, 7], [823, 738, 749]]]
+_C_OUT = [16, 24, 24, 24, 24, 40, 40, 40, 40, 80, 80, 80, 80, 96, 96, 96, 96, 192, 192, 192, 192, 320]
+_C_STRIDE = [1, 2, 1, 1, 1, 2, 1, 1, 1, 2, 1, 1, 1, 1, 1, 1, 1, 2, 1, 1, 1, 1]
+ATOMNAS_C_PLUS = dict(           # apps/searched/atomnas_c/atomnas_c+.yml (BASELINE config 4): searched widths,
+    num_classes=1000, input_channel=32, last_channel=1280, width_mult=1.0, round_nearest=8,   # SE 0.5, Swish
+    inverted_residual_setting=[[c, 1, s, ks, hid, i > 0] for i, (c, s, (ks, hid)) in
+                               enumerate(zip(_C_OUT, _C_STRIDE, SEARCHED_C))],
+    dropout_ratio=0.28, se_ratio=0.5, batch_norm_momentum=0.01, batch_norm_epsilon=1e-3, active_fn="nn.Swish",
+    block="InvertedResidualChannelsFused")
+MODELS["atomnas_c_plus"] = ("AtomNAS-C+ (apps/searched/atomnas_c/atomnas_c+.yml: searched widths, SE 0.5, Swish, "
+                            "fused block)", ATOMNAS_C_PLUS)
 PER_GPU_BATCH = 256
 IMAGE = 224
 RHO = 1.0e-4            # post-warm-up L1 weight (atomnas_c.yml prune_params.rho): pruning term active
@@ -106,7 +116,8 @@ def build_model(kwargs=ATOMNAS_C_SUPERNET):
     from atomnas_b200 import mobilenet_base as mb
     from atomnas_b200 import mobilenet_supernet as ms
     torch.manual_seed(1995)
-    model = ms.MobileNetV2(**kwargs, input_size=IMAGE)
+    cls = ms.MobileNetSearched if len(kwargs["inverted_residual_setting"][0]) == 6 else ms.MobileNetV2
+    model = cls(**kwargs, input_size=IMAGE)
     model.apply(mb.init_weights_mnas)
     return model
 
@@ -115,7 +126,9 @@ def build_trainer(model, world, use_graph):
     from atomnas_b200 import prune
     from atomnas_b200.trainer import Trainer
     prune.profile_macs(model, IMAGE)
-    info = prune.get_bn_to_prune(model, {"bn_prune_filter": "expansion_only_skip_expand1"}, verbose=False)
+    searched = hasattr(list(model.get_named_block_list().values())[0], "depth_ops")
+    info = prune.get_bn_to_prune(model, {"bn_prune_filter": None if searched else "expansion_only_skip_expand1"},
+                                 verbose=False)
     gb = PER_GPU_BATCH * world
     tr = Trainer(model, lr=0.016 * gb / 256, alpha=0.9, momentum=0.9, eps=1e-3, eps_inside_sqrt=True,
                  weight_decay=WEIGHT_DECAY, label_smoothing=0.1, ema_decay=0.9999 ** (gb / 4096.0),

@@ -1,0 +1,116 @@
+"""GPU parity of InvertedResidualChannelsFused + SqueezeAndExcitation (BASELINE config 4, AtomNAS-C+).
+
+  * one block against what the unmodified reference produced (tests/golden/tiny_fused_*.pt, fp32):
+    output and input gradient <= 3e-2 of max, every parameter gradient <= 5e-2 relative L2 (bf16
+    storage between kernels vs the fp32 reference; the SE FCs and all reductions are fp32), BN
+    running statistics <= 2e-2;
+  * the full AtomNAS-C+ network (apps/searched/atomnas_c/atomnas_c+.yml: searched widths, SE 0.5,
+    Swish, Fused block) at 224 against the unmodified reference modules (oracle/_ref) on the host:
+    logits <= 4e-2 of max, loss <= 1e-2 relative, gradient relative L2 median <= 6e-2.
+"""
+import collections
+import os
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+from atomnas_b200 import fused_block as fb  # noqa: E402
+from atomnas_b200 import mobilenet_base as mb  # noqa: E402
+from atomnas_b200 import mobilenet_supernet as ms  # noqa: E402
+from atomnas_b200 import prune  # noqa: E402
+from atomnas_b200.trainer import Trainer  # noqa: E402
+
+G = os.path.join(ROOT, "tests", "golden")
+DEV = "cuda"
+
+
+def rel(a, b):
+    return ((a - b).norm() / b.norm().clamp_min(1e-20)).item()
+
+
+@pytest.mark.parametrize("name", ["tiny_fused_se_swish", "tiny_fused_relu_s2"])
+def test_fused_block_vs_reference_golden(name):
+    g = torch.load(os.path.join(G, name + ".pt"), weights_only=False)
+    a = g["args"]
+    blk = fb.InvertedResidualChannelsFused(a["inp"], a["oup"], a["stride"], a["channels"], a["kernel_sizes"],
+                                           a["expand"], active_fn=mb.get_active_fn(a["active_fn"]),
+                                           batch_norm_kwargs={"momentum": a["bn_momentum"], "eps": a["bn_eps"]},
+                                           se_ratio=a["se_ratio"])
+    blk.load_state_dict(g["state0"])
+    blk = blk.cuda().train()
+    x = g["x"].to(DEV).requires_grad_(True)
+    y = blk(x)
+    (y * g["w"].to(DEV)).sum().backward()
+    ref = g["y"].to(DEV)
+    assert (y - ref).abs().max().item() <= 3e-2 * ref.abs().max().item() + 1e-2
+    rdx = g["dx"].to(DEV)
+    assert (x.grad - rdx).abs().max().item() <= 3e-2 * rdx.abs().max().item() + 1e-2
+    gmax = max(v.norm().item() for v in g["grads"].values())
+    errs = {n: rel(p.grad, g["grads"][n].to(DEV)) for n, p in blk.named_parameters()
+            if g["grads"][n].norm().item() > 1e-3 * gmax}
+    print(name, {k: round(v, 4) for k, v in errs.items()})
+    assert max(errs.values()) <= 5e-2, max(errs.items(), key=lambda kv: kv[1])
+    sd = blk.state_dict()
+    for n, v in g["state_after"].items():
+        if "running" in n:
+            torch.testing.assert_close(sd[n].cpu(), v, rtol=2e-2, atol=2e-3)
+        elif "num_batches" in n:
+            assert int(sd[n]) == int(v)
+
+
+def test_atomnas_c_plus_network_vs_unmodified_reference():
+    from oracle import ref_runner as RR
+    if not RR.available():
+        pytest.skip("oracle/_ref not staged (python oracle/make_ref.py where /root/reference exists)")
+    R = RR.load()
+    _, kw = bench.MODELS["atomnas_c_plus"]
+    kw = dict(kw, dropout_ratio=0.0)
+    B, S = 4, 224
+    torch.manual_seed(3)
+    ref = R.sn.Model(**kw, input_size=S)
+    ref.apply(R.mb.init_weights_mnas)
+    gen = torch.Generator().manual_seed(4)
+    with torch.no_grad():
+        for m in ref.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.weight.copy_(1.0 + 0.1 * torch.randn(m.weight.shape, generator=gen))
+                m.bias.copy_(0.05 * torch.randn(m.bias.shape, generator=gen))
+            if isinstance(m, torch.nn.Conv2d) and m.bias is not None:
+                m.bias.copy_(0.1 * torch.randn(m.bias.shape, generator=gen))
+    state0 = collections.OrderedDict((k, v.clone()) for k, v in ref.state_dict().items())
+    x = torch.randn(B, 3, S, S, generator=gen)
+    y = torch.randint(0, 1000, (B,), generator=gen)
+    crit = R.optim.CrossEntropyLabelSmooth(1000, 0.1, reduction="none")
+    ref.train()
+    torch.set_num_threads(min(32, os.cpu_count() or 8))
+    lo = ref(x)
+    loss_ref = crit(lo, y).mean()
+    loss_ref.backward()
+    model = ms.MobileNetSearched(**kw, input_size=S)
+    assert list(model.state_dict().keys()) == list(state0.keys())
+    model.load_state_dict(state0)
+    model = model.cuda().train()
+    assert prune.profile_macs(model, S) > 0
+    logits = model(x.to(DEV))
+    from atomnas_b200 import optim as aopt
+    loss = aopt.CrossEntropyLabelSmooth(1000, 0.1, reduction="none")(logits, y.to(DEV)).mean()
+    loss.backward()
+    assert (logits.detach().cpu() - lo.detach()).abs().max().item() <= 4e-2 * lo.abs().max().item() + 2e-2
+    assert abs(loss.item() - loss_ref.item()) <= 1e-2 * abs(loss_ref.item())
+    named_ref = dict(ref.named_parameters())
+    gmax = max(p.grad.norm().item() for p in named_ref.values())
+    errs = torch.tensor(sorted(rel(p.grad.detach().cpu(), named_ref[n].grad) for n, p in model.named_parameters()
+                               if named_ref[n].grad.norm().item() > 1e-3 * gmax))
+    print("AtomNAS-C+ grad rel-L2 vs reference: median %.4f p90 %.4f max %.4f (%d tensors)" % (
+        errs.median(), errs[int(0.9 * (len(errs) - 1))], errs.max(), len(errs)))
+    assert errs.median().item() <= 6e-2
+    # the fused step (graph + eager) runs on this network too
+    tr = Trainer(model, lr=0.016, weight_decay=1e-5, label_smoothing=0.1, ema_decay=0.999)
+    l1 = tr.step(x.to(DEV), y.to(DEV))
+    assert torch.isfinite(l1).all() and abs(l1.mean().item() - loss_ref.item()) <= 2e-2 * abs(loss_ref.item())

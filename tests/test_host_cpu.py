@@ -264,8 +264,8 @@ def test_dropin_shims_build_the_yaml_model_like_the_reference():
 @pytest.mark.parametrize("name", ["tiny_fused_se_swish", "tiny_fused_relu_s2"])
 def test_fused_block_surface_matches_reference_state_dict(name):
     """The AtomNAS-C+ block's module surface (scope row 8f-1): same state_dict keys / shapes as the
-    reference's InvertedResidualChannelsFused (+SE), loads its weights, and refuses to run until its
-    kernels exist (no silent PyTorch fallback)."""
+    reference's InvertedResidualChannelsFused (+SE), loads its weights, and refuses CPU tensors (the
+    block runs on the sm_100a kernels only -- no silent PyTorch fallback)."""
     from atomnas_b200 import fused_block as fb
     g = torch.load(os.path.join(G, name + ".pt"), weights_only=False)
     a = g["args"]
@@ -279,5 +279,5 @@ def test_fused_block_surface_matches_reference_state_dict(name):
         assert tuple(sd[k].shape) == tuple(v.shape), k
     assert blk.load_state_dict(g["state0"]).missing_keys == []
     assert list(blk.get_named_depthwise_bn("p").keys()) == ["p.depth_ops.%d.1.1" % i for i in range(len(a["channels"]))]
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
         blk(g["x"])
