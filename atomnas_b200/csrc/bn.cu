@@ -91,37 +91,60 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int rows,
 }
 
 // out = act(a1[c]*x1 + a2[c]*x2 + a3[c]); a1/a2 default 1, a3 default 0, x2 optional.
-__global__ void affine_act_kernel(const __nv_bfloat16* __restrict__ x1, long long ld1,
-                                  const __nv_bfloat16* __restrict__ x2, long long ld2,
-                                  const float* __restrict__ a1, const float* __restrict__ a2,
-                                  const float* __restrict__ a3, int act, __nv_bfloat16* out,
-                                  long long ldo, long long M, int C) {
-  const int ncg = C / 8;
-  const long long total = M * ncg;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long row = i / ncg;
-    const int ch = static_cast<int>(i % ncg) * 8;
-    float c1[8], c2[8], c3[8];
-    load_coef8(a1, ch, C, c1, 1.f);
-    load_coef8(a2, ch, C, c2, 1.f);
-    load_coef8(a3, ch, C, c3, 0.f);
-    const uint4 v = ldg_nc_v4(x1 + row * ld1 + ch);
-    uint4 w = make_uint4(0, 0, 0, 0);
-    if (x2 != nullptr) w = ldg_nc_v4(x2 + row * ld2 + ch);
-    const uint32_t vi[4] = {v.x, v.y, v.z, v.w}, wi[4] = {w.x, w.y, w.z, w.w};
-    uint32_t o[4];
+// A thread owns ONE 8-channel group (its coefficients stay in registers) and walks rows with a
+// stride; 4 rows are in flight per thread (loads issued before the first use).
+constexpr int kAffUnroll = 4;
+__device__ __forceinline__ uint4 affine8(const uint4 v, const uint4 w, const bool two, const float* c1,
+                                         const float* c2, const float* c3, const int act) {
+  const uint32_t vi[4] = {v.x, v.y, v.z, v.w}, wi[4] = {w.x, w.y, w.z, w.w};
+  uint32_t o[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      float lo = fmaf(c1[2 * e], bf16_lo(vi[e]), c3[2 * e]);
-      float hi = fmaf(c1[2 * e + 1], bf16_hi(vi[e]), c3[2 * e + 1]);
-      if (x2 != nullptr) {
-        lo = fmaf(c2[2 * e], bf16_lo(wi[e]), lo);
-        hi = fmaf(c2[2 * e + 1], bf16_hi(wi[e]), hi);
-      }
-      o[e] = pack_bf16(act_fwd(lo, act), act_fwd(hi, act));
+  for (int e = 0; e < 4; ++e) {
+    float lo = fmaf(c1[2 * e], bf16_lo(vi[e]), c3[2 * e]);
+    float hi = fmaf(c1[2 * e + 1], bf16_hi(vi[e]), c3[2 * e + 1]);
+    if (two) {
+      lo = fmaf(c2[2 * e], bf16_lo(wi[e]), lo);
+      hi = fmaf(c2[2 * e + 1], bf16_hi(wi[e]), hi);
     }
-    stg_v4(out + row * ldo + ch, make_uint4(o[0], o[1], o[2], o[3]));
+    o[e] = pack_bf16(act_fwd(lo, act), act_fwd(hi, act));
+  }
+  return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+__global__ void __launch_bounds__(256) affine_act_kernel(const __nv_bfloat16* __restrict__ x1, long long ld1,
+                                                         const __nv_bfloat16* __restrict__ x2, long long ld2,
+                                                         const float* __restrict__ a1, const float* __restrict__ a2,
+                                                         const float* __restrict__ a3, int act, __nv_bfloat16* out,
+                                                         long long ldo, long long M, int C) {
+  const int ncg = C / 8;
+  const int cgb = min(ncg, 32);                 // channel groups per CTA (blockIdx.y selects the block)
+  const int lanes = 256 / cgb;                  // row lanes per CTA
+  const int lcg = threadIdx.x % cgb, rl = threadIdx.x / cgb;
+  const int cg = blockIdx.y * cgb + lcg;
+  if (cg >= ncg || rl >= lanes) return;
+  const int ch = cg * 8;
+  float c1[8], c2[8], c3[8];
+  load_coef8(a1, ch, C, c1, 1.f);
+  load_coef8(a2, ch, C, c2, 1.f);
+  load_coef8(a3, ch, C, c3, 0.f);
+  const bool two = x2 != nullptr;
+  const long long stride = static_cast<long long>(gridDim.x) * lanes;
+  long long r = static_cast<long long>(blockIdx.x) * lanes + rl;
+  for (; r + (kAffUnroll - 1) * stride < M; r += kAffUnroll * stride) {
+    uint4 v[kAffUnroll], w[kAffUnroll];
+#pragma unroll
+    for (int k = 0; k < kAffUnroll; ++k) {
+      v[k] = ldg_nc_v4(x1 + (r + k * stride) * ld1 + ch);
+      w[k] = two ? ldg_nc_v4(x2 + (r + k * stride) * ld2 + ch) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int k = 0; k < kAffUnroll; ++k)
+      stg_v4(out + (r + k * stride) * ldo + ch, affine8(v[k], w[k], two, c1, c2, c3, act));
+  }
+  for (; r < M; r += stride) {
+    const uint4 v = ldg_nc_v4(x1 + r * ld1 + ch);
+    const uint4 w = two ? ldg_nc_v4(x2 + r * ld2 + ch) : make_uint4(0, 0, 0, 0);
+    stg_v4(out + r * ldo + ch, affine8(v, w, two, c1, c2, c3, act));
   }
 }
 
@@ -309,10 +332,14 @@ extern "C" int an_affine_act(const void* x1, long long ld1, const void* x2, long
                              long long ldo, long long M, int C, void* stream) {
   AN_REQUIRE(x1 && out && M > 0 && C > 0 && C % 8 == 0 && ld1 % 8 == 0 && ldo % 8 == 0 && (x2 == nullptr || ld2 % 8 == 0),
              "an_affine_act: bad arguments");
-  const long long total = M * (C / 8);
-  long long blocks = (total + 255) / 256;
-  if (blocks > 16LL * sm_count()) blocks = 16LL * sm_count();
-  affine_act_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  const int ncg = C / 8, cgb = ncg < 32 ? ncg : 32, lanes = 256 / cgb;
+  const int ygrid = (ncg + cgb - 1) / cgb;
+  long long xgrid = (M + static_cast<long long>(lanes) * kAffUnroll - 1) / (static_cast<long long>(lanes) * kAffUnroll);
+  const long long cap = (8LL * sm_count() + ygrid - 1) / ygrid;         // ~8 CTAs of 256 threads per SM in total
+  if (xgrid > cap) xgrid = cap;
+  if (xgrid < 1) xgrid = 1;
+  dim3 grid(static_cast<unsigned>(xgrid), ygrid);
+  affine_act_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(x1), ld1, reinterpret_cast<const __nv_bfloat16*>(x2), ld2,
       a1, a2, a3, act, reinterpret_cast<__nv_bfloat16*>(out), ldo, M, C);
   AN_CHECK_LAUNCH();

@@ -91,7 +91,8 @@ __device__ __forceinline__ float2 xform(const float2 x, const float2 xs, const f
 
 struct Params {
   CUtensorMap tm_in;                  // streamed operand: x (forward / wgrad) or dd (data gradient)
-  CUtensorMap tm_dd;                  // wgrad: dd rows, box {64, TC*nwc, R, 1}
+  CUtensorMap tm_dd;                  // wgrad: dd rows, box {64, TC*nwc, R, 1}; data gradient: eraw rows
+  CUtensorMap tm_in2, tm_dd2;         // the same with 2-image boxes (tail channel blocks, see `tail`)
   const float* w;                     // [k*k][C] tap-major fp32
   __nv_bfloat16* out;                 // forward: y; data gradient: ge
   long long ldo;
@@ -106,6 +107,8 @@ struct Params {
   int H, W;                           // streamed tensor's spatial size
   int Ho, Wo;                         // written tensor's spatial size (wgrad: the dd size)
   int nwc, PW, depth, nch, ipb;
+  int tail;                           // the last channel block has <= 32 channels: its CTAs put TWO images
+                                      // in one warp (lanes 16-31 = the next image), halving their count
 };
 
 constexpr int kThreads = 256;         // 7 compute warps + the producer warp
@@ -169,39 +172,51 @@ __global__ void __launch_bounds__(kThreads, MB) dw2_conv(const __grid_constant__
   using G = Geom<K, S, TC>;
   constexpr int P = G::P, U = G::U, R = G::R, NX = G::NX;
   constexpr bool EBN = MODE != 0, SWISH = MODE == 2;
-  const int ncomp = p.nwc, D = p.depth, PW = p.PW;
+  const int ncomp = p.nwc, PW = p.PW;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t in_bytes = static_cast<uint32_t>(U * PW * 128);
-  const uint32_t e_bytes = EBN ? static_cast<uint32_t>(U * TC * p.nwc * 128) : 0u;   // U rows of eraw under the strip
-  const uint32_t stage_bytes = in_bytes + e_bytes;
-  uint64_t *full, *empty;
-  ring_setup(dsm, D, stage_bytes, full, empty, ncomp, &p.tm_in, EBN ? &p.tm_dd : nullptr);
-  float* red = reinterpret_cast<float*>(empty + D);                     // [ncomp][2][64]
   const int cb0 = blockIdx.y * 64;
+  // Tail channel block (<= 32 channels = 16 lanes): a warp carries TWO images, lanes 16-31 the
+  // second one.  Such CTAs own 2*ipb images (half of them have nothing to do), load two-image TMA
+  // boxes and use half the ring depth (same shared-memory footprint).
+  const bool tail = p.tail != 0 && (p.C - cb0) <= 32;
+  const int nim = tail ? 2 : 1;
+  const int D = tail ? p.depth / 2 : p.depth;
+  const uint32_t img_bytes = static_cast<uint32_t>(U * PW * 128);
+  const uint32_t eimg_bytes = EBN ? static_cast<uint32_t>(U * TC * p.nwc * 128) : 0u;   // U rows of eraw under the strip
+  const uint32_t in_bytes = img_bytes * nim;
+  const uint32_t stage_bytes = (img_bytes + eimg_bytes) * nim;
+  uint64_t *full, *empty;
+  ring_setup(dsm, p.depth, img_bytes + eimg_bytes, full, empty, ncomp, tail ? &p.tm_in2 : &p.tm_in,
+             EBN ? (tail ? &p.tm_dd2 : &p.tm_dd) : nullptr);
+  float* red = reinterpret_cast<float*>(empty + p.depth);               // [ncomp][2][64]
   const int ox0 = blockIdx.x * TC * p.nwc;
-  const int n0 = blockIdx.z * p.ipb;
-  const int nimg = min(p.ipb, p.B - n0);
+  const int n0 = blockIdx.z * p.ipb * nim;
+  const int ngrp = (n0 < p.B) ? min(p.ipb, (p.B - n0 + nim - 1) / nim) : 0;     // image (pair) iterations
 
   if (warp == ncomp) {
     // ------------------------------------------------------------------ producer
     if (lane == 0) {
+      const CUtensorMap* tin = tail ? &p.tm_in2 : &p.tm_in;
+      const CUtensorMap* tdd = tail ? &p.tm_dd2 : &p.tm_dd;
       uint32_t it = 0;
-      for (int gi = 0; gi < nimg; ++gi)
+      for (int gi = 0; gi < ngrp; ++gi)
         for (int c = 0; c < p.nch; ++c, ++it) {
           const int st = it % D;
           mbar_wait(&empty[st], ((it / D) & 1) ^ 1);
           mbar_expect_tx(&full[st], stage_bytes);
           uint8_t* sp = dsm + (size_t)st * stage_bytes;
-          tma_load_4d(sp, &p.tm_in, &full[st], cb0, S * ox0 - P, c * U, n0 + gi);
+          tma_load_4d(sp, tin, &full[st], cb0, S * ox0 - P, c * U, n0 + gi * nim);
           if (EBN)       // output rows c*U-P .. c*U+U-1-P finish in this stage: their eraw rows
-            tma_load_4d(sp + in_bytes, &p.tm_dd, &full[st], cb0, ox0, c * U - P, n0 + gi);
+            tma_load_4d(sp + in_bytes, tdd, &full[st], cb0, ox0, c * U - P, n0 + gi * nim);
         }
     }
     return;
   }
 
   // -------------------------------------------------------------------- consumers
-  const int ch = cb0 + 2 * lane;
+  const int half = tail ? (lane >> 4) : 0;             // which image of the pair this lane works on
+  const int clane = tail ? (lane & 15) : lane;         // channel-pair index inside the block
+  const int ch = cb0 + 2 * clane;
   const bool ch_ok = ch < p.C;
   float2 w[K * K];
 #pragma unroll
@@ -255,23 +270,24 @@ __global__ void __launch_bounds__(kThreads, MB) dw2_conv(const __grid_constant__
     }
   }
   const bool edge = XF == 2 && cmask != ((1u << NX) - 1u);
-  const bool live = (oxw < p.Wo) && ch_ok;
-  const uint32_t* pbase = reinterpret_cast<const uint32_t*>(dsm) + (S * TC * warp) * 32 + lane;
-  const uint32_t* ebase = reinterpret_cast<const uint32_t*>(dsm + in_bytes) + (TC * warp) * 32 + lane;
+  const bool col_live = (oxw < p.Wo) && ch_ok;
+  const uint32_t* pbase = reinterpret_cast<const uint32_t*>(dsm) + half * (img_bytes / 4) + (S * TC * warp) * 32 + clane;
+  const uint32_t* ebase = reinterpret_cast<const uint32_t*>(dsm) + half * (eimg_bytes / 4) + (TC * warp) * 32 + clane;
   const int rowstride = PW * 32;                                        // words
   const int erowstride = TC * p.nwc * 32;
   const long long ldo2 = p.ldo * 2;                                     // bytes between output columns
   const long long orow2 = (long long)p.Wo * ldo2;                       // bytes per output row
   uint32_t it = 0;
-  for (int gi = 0; gi < nimg; ++gi) {
-    const int n = n0 + gi;
+  for (int gi = 0; gi < ngrp; ++gi) {
+    const int n = n0 + gi * nim + half;
+    const bool live = col_live && n < p.B;
     char* op = reinterpret_cast<char*>(p.out + ((long long)n * p.Ho * p.Wo + oxw) * p.ldo + ch);   // output row 0
     for (int c = 0; c < p.nch; ++c, ++it) {
       const int st = it % D;
       mbar_wait(&full[st], (it / D) & 1);
       if (live) {
         const uint32_t* prow = pbase + (size_t)st * (stage_bytes / 4);
-        const uint32_t* erow = ebase + (size_t)st * (stage_bytes / 4);
+        const uint32_t* erow = ebase + ((size_t)st * stage_bytes + in_bytes) / 4;
         uint32_t xr[NX];
 #pragma unroll
         for (int cc = 0; cc < NX; ++cc) xr[cc] = prow[cc * 32];
@@ -349,14 +365,22 @@ __global__ void __launch_bounds__(kThreads, MB) dw2_conv(const __grid_constant__
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[st]);
     }
-    if (gi + 1 < nimg) {              // partial sums of rows below the image never complete: clear
+    if (gi + 1 < ngrp) {              // partial sums of rows below the image never complete: clear
 #pragma unroll
       for (int s = 0; s < R; ++s)
 #pragma unroll
         for (int j = 0; j < TC; ++j) acc[s][j] = make_float2(0.f, 0.f);
     }
   }
-  if (p.stats_part != nullptr) write_stats(p, red, warp, lane, ncomp, cb0, st1, st2);
+  if (p.stats_part != nullptr) {
+    if (tail) {                       // both halves of the warp hold statistics of the same channels
+      st1.x += __shfl_down_sync(0xffffffffu, st1.x, 16);
+      st1.y += __shfl_down_sync(0xffffffffu, st1.y, 16);
+      st2.x += __shfl_down_sync(0xffffffffu, st2.x, 16);
+      st2.y += __shfl_down_sync(0xffffffffu, st2.y, 16);
+    }
+    write_stats(p, red, warp, lane, ncomp, cb0, st1, st2);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -369,50 +393,58 @@ __global__ void __launch_bounds__(kThreads, ((K == 3 || K == 5) && TC == 4) ? 2 
   extern __shared__ __align__(128) uint8_t dsm[];
   using G = Geom<K, S, TC>;
   constexpr int P = G::P, U = G::U, R = G::R, NX = G::NX;
-  const int ncomp = p.nwc, D = p.depth, PW = p.PW, TW = TC * p.nwc;
+  const int ncomp = p.nwc, PW = p.PW, TW = TC * p.nwc;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t u_bytes = static_cast<uint32_t>(U * PW * 128), d_bytes = static_cast<uint32_t>(R * TW * 128);
-  const uint32_t stage_bytes = u_bytes + d_bytes;
+  const int cb0 = blockIdx.y * 64;
+  const bool tail = p.tail != 0 && (p.C - cb0) <= 32;         // two images per warp (see dw2_conv)
+  const int nim = tail ? 2 : 1;
+  const int D = tail ? p.depth / 2 : p.depth;
+  const uint32_t u_img = static_cast<uint32_t>(U * PW * 128), d_img = static_cast<uint32_t>(R * TW * 128);
+  const uint32_t u_bytes = u_img * nim;
+  const uint32_t stage_bytes = (u_img + d_img) * nim;
   const size_t red_bytes = (size_t)ncomp * K * K * 64 * 4;
-  const size_t ring_bytes = (size_t)D * stage_bytes;
+  const size_t ring_bytes = (size_t)p.depth * (u_img + d_img);
   // barriers live after max(ring, reduction scratch): the scratch reuses the ring after the stream
   uint8_t* bars = dsm + (ring_bytes > red_bytes ? ring_bytes : red_bytes);
   uint64_t* full = reinterpret_cast<uint64_t*>(bars);
-  uint64_t* empty = full + D;
+  uint64_t* empty = full + p.depth;
   if (threadIdx.x == 0) {
     if (smem_u32(dsm) & 127u) __trap();
-    for (int s = 0; s < D; ++s) {
+    for (int s = 0; s < p.depth; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], ncomp);
     }
     mbar_fence_init();
-    tma_prefetch_desc(&p.tm_in);
-    tma_prefetch_desc(&p.tm_dd);
+    tma_prefetch_desc(tail ? &p.tm_in2 : &p.tm_in);
+    tma_prefetch_desc(tail ? &p.tm_dd2 : &p.tm_dd);
   }
   __syncthreads();
   float* red = reinterpret_cast<float*>(dsm);
-  const int cb0 = blockIdx.y * 64;
   const int ox0 = blockIdx.x * TW;                                      // dd column origin of the strip
-  const int n0 = blockIdx.z * p.ipb;
-  const int nimg = min(p.ipb, p.B - n0);
+  const int n0 = blockIdx.z * p.ipb * nim;
+  const int ngrp = (n0 < p.B) ? min(p.ipb, (p.B - n0 + nim - 1) / nim) : 0;
 
   if (warp == ncomp) {
     if (lane == 0) {
+      const CUtensorMap* tin = tail ? &p.tm_in2 : &p.tm_in;
+      const CUtensorMap* tdd = tail ? &p.tm_dd2 : &p.tm_dd;
       uint32_t it = 0;
-      for (int gi = 0; gi < nimg; ++gi)
+      for (int gi = 0; gi < ngrp; ++gi)
         for (int c = 0; c < p.nch; ++c, ++it) {
           const int st = it % D;
           mbar_wait(&empty[st], ((it / D) & 1) ^ 1);
           mbar_expect_tx(&full[st], stage_bytes);
           uint8_t* sp = dsm + (size_t)st * stage_bytes;
-          tma_load_4d(sp, &p.tm_in, &full[st], cb0, S * ox0 - P, c * U - P, n0 + gi);
-          tma_load_4d(sp + u_bytes, &p.tm_dd, &full[st], cb0, ox0, c * R, n0 + gi);
+          tma_load_4d(sp, tin, &full[st], cb0, S * ox0 - P, c * U - P, n0 + gi * nim);
+          tma_load_4d(sp + u_bytes, tdd, &full[st], cb0, ox0, c * R, n0 + gi * nim);
         }
     }
     return;
   }
 
-  const int ch = cb0 + 2 * lane;
+  const int half = tail ? (lane >> 4) : 0;
+  const int clane = tail ? (lane & 15) : lane;
+  const int ch = cb0 + 2 * clane;
   const bool ch_ok = ch < p.C;
   float2 xs = make_float2(1.f, 1.f), xh = make_float2(0.f, 0.f);
   float xlo = -INFINITY, xhi = INFINITY;
@@ -444,18 +476,19 @@ __global__ void __launch_bounds__(kThreads, ((K == 3 || K == 5) && TC == 4) ? 2 
     }
   }
   const bool edge = XF == 2 && cmask != ((1u << NX) - 1u);
-  const bool live = (oxw < p.Wo) && ch_ok;
-  const uint32_t* ubase = reinterpret_cast<const uint32_t*>(dsm) + (S * TC * warp) * 32 + lane;
-  const uint32_t* dbase = reinterpret_cast<const uint32_t*>(dsm + u_bytes) + (TC * warp) * 32 + lane;
+  const bool col_live = (oxw < p.Wo) && ch_ok;
+  const uint32_t* ubase = reinterpret_cast<const uint32_t*>(dsm) + half * (u_img / 4) + (S * TC * warp) * 32 + clane;
+  const uint32_t* dbase = reinterpret_cast<const uint32_t*>(dsm) + half * (d_img / 4) + (TC * warp) * 32 + clane;
   const int rowstride = PW * 32, drow = TW * 32;
   uint32_t it = 0;
-  for (int gi = 0; gi < nimg; ++gi) {
+  for (int gi = 0; gi < ngrp; ++gi) {
+    const bool live = col_live && (n0 + gi * nim + half) < p.B;
     for (int c = 0; c < p.nch; ++c, ++it) {
       const int st = it % D;
       mbar_wait(&full[st], (it / D) & 1);
       if (live) {
         const uint32_t* urow = ubase + (size_t)st * (stage_bytes / 4);
-        const uint32_t* ddrow = dbase + (size_t)st * (stage_bytes / 4);
+        const uint32_t* ddrow = dbase + ((size_t)st * stage_bytes + u_bytes) / 4;
         uint32_t xr[NX];
 #pragma unroll
         for (int cc = 0; cc < NX; ++cc) xr[cc] = urow[cc * 32];
@@ -466,8 +499,9 @@ __global__ void __launch_bounds__(kThreads, ((K == 3 || K == 5) && TC == 4) ? 2 
 #pragma unroll
           for (int cc = 0; cc < NX; ++cc) x[cc] = unpack2(xr[cc]);
           if (u + 1 < U) {
+            urow += rowstride;
 #pragma unroll
-            for (int cc = 0; cc < NX; ++cc) xr[cc] = urow[(u + 1) * rowstride + cc * 32];
+            for (int cc = 0; cc < NX; ++cc) xr[cc] = urow[cc * 32];
           }
           if (u % S == 0) {                         // dd row o = c*R + u/S enters the register ring
 #pragma unroll
@@ -500,11 +534,18 @@ __global__ void __launch_bounds__(kThreads, ((K == 3 || K == 5) && TC == 4) ? 2 
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[st]);
     }
-    if (gi + 1 < nimg) {                            // dd rows of this image must not pair with the next
+    if (gi + 1 < ngrp) {                            // dd rows of this image must not pair with the next
 #pragma unroll
       for (int s = 0; s < R; ++s)
 #pragma unroll
         for (int j = 0; j < TC; ++j) dr[s][j] = make_float2(0.f, 0.f);
+    }
+  }
+  if (tail) {                                       // both halves accumulated the same channels
+#pragma unroll
+    for (int t = 0; t < K * K; ++t) {
+      acc[t].x += __shfl_down_sync(0xffffffffu, acc[t].x, 16);
+      acc[t].y += __shfl_down_sync(0xffffffffu, acc[t].y, 16);
     }
   }
   // every stage has been consumed by this warp; wait for the others before reusing the ring
@@ -531,7 +572,7 @@ __global__ void __launch_bounds__(kThreads, ((K == 3 || K == 5) && TC == 4) ? 2 
 // ------------------------------------------------------------------------------------------------
 struct Cfg {
   int tc, nwc, strips, ipb, gz, nch, PW, depth, threads, parts, minb;
-  bool ragged;
+  bool ragged, tail;
   size_t smem;
 };
 
@@ -582,6 +623,9 @@ static Cfg make_cfg(int kind, int B, int C, int Ht, int Wt, int Hin, int k, int 
   if (depth > c.nch + 1) depth = c.nch + 1;
   if (depth < 2) depth = 2;
   c.depth = depth;
+  // tail channel block with <= 32 channels: two images per warp, needs >= 2 two-image stages
+  const int crem = C % 64;
+  c.tail = crem != 0 && crem <= 32 && depth >= 4 && B >= 2 && getenv("AN_DW_NOTAIL") == nullptr;
   size_t ring = (size_t)depth * stage;
   if (kind == 1) {
     const size_t red = (size_t)c.nwc * k * k * 64 * 4;
@@ -623,6 +667,7 @@ static int launch(Kernel kernel, const Params& p, const Cfg& c, cudaStream_t st)
 static void fill(Params& p, const Cfg& c, int B, int C) {
   p.B = B; p.C = C;
   p.nwc = c.nwc; p.PW = c.PW; p.depth = c.depth; p.nch = c.nch; p.ipb = c.ipb;
+  p.tail = c.tail ? 1 : 0;
 }
 
 template <int K, int S, int MODE, int XF>
@@ -684,6 +729,8 @@ static int fwd(const an_dw_fwd_args* a, cudaStream_t st) {
   const int xf = xf_mode(a->scale, a->act);
   // ReLU on load: out-of-image elements are NaN-filled and become 0 through max(., 0)
   if (int e = make_tmap_bf16_nhwc(&p.tm_in, a->x, a->C, a->W, a->H, a->B, a->ldx, 64, c.PW, U, 1, xf == 1)) return e;
+  if (c.tail)
+    if (int e = make_tmap_bf16_nhwc(&p.tm_in2, a->x, a->C, a->W, a->H, a->B, a->ldx, 64, c.PW, U, 2, xf == 1)) return e;
   fill(p, c, a->B, a->C);
   p.w = a->w;
   p.out = reinterpret_cast<__nv_bfloat16*>(a->y); p.ldo = a->ldy;
@@ -708,6 +755,10 @@ static int bwd_data1(const an_dw_bwd_args* a, cudaStream_t st) {      // stride 
   memset(&p, 0, sizeof(p));
   if (int e = make_tmap_bf16_nhwc(&p.tm_in, a->g, a->C, a->W, a->H, a->B, a->ldg, 64, c.PW, a->k, 1)) return e;
   if (int e = make_tmap_bf16_nhwc(&p.tm_dd, a->eraw, a->C, a->W, a->H, a->B, a->lde, 64, c.tc * c.nwc, a->k, 1)) return e;
+  if (c.tail) {
+    if (int e = make_tmap_bf16_nhwc(&p.tm_in2, a->g, a->C, a->W, a->H, a->B, a->ldg, 64, c.PW, a->k, 2)) return e;
+    if (int e = make_tmap_bf16_nhwc(&p.tm_dd2, a->eraw, a->C, a->W, a->H, a->B, a->lde, 64, c.tc * c.nwc, a->k, 2)) return e;
+  }
   fill(p, c, a->B, a->C);
   p.w = a->w;
   p.out = reinterpret_cast<__nv_bfloat16*>(a->ge); p.ldo = a->ldge;
@@ -735,6 +786,10 @@ static int wgrad(const an_dw_bwd_args* a, float* partials, cudaStream_t st) {
   const int xf = xf_mode(a->e_scale, a->act);
   if (int e = make_tmap_bf16_nhwc(&p.tm_in, a->eraw, a->C, a->W, a->H, a->B, a->lde, 64, c.PW, U, 1, xf == 1)) return e;
   if (int e = make_tmap_bf16_nhwc(&p.tm_dd, a->g, a->C, Wo, Ho, a->B, a->ldg, 64, c.tc * c.nwc, R, 1)) return e;
+  if (c.tail) {
+    if (int e = make_tmap_bf16_nhwc(&p.tm_in2, a->eraw, a->C, a->W, a->H, a->B, a->lde, 64, c.PW, U, 2, xf == 1)) return e;
+    if (int e = make_tmap_bf16_nhwc(&p.tm_dd2, a->g, a->C, Wo, Ho, a->B, a->ldg, 64, c.tc * c.nwc, R, 2)) return e;
+  }
   fill(p, c, a->B, a->C);
   p.wpart = partials;
   p.x_scale = a->e_scale; p.x_shift = a->e_shift; p.act = a->act;

@@ -21,39 +21,59 @@ namespace an {
 constexpr int kSeThreads = 256;
 
 // pooled[b, c] = mean over HW of act(scale*x + shift); with D != NULL: sum over HW of D * act(...)
-// grid (C/64 blocks of 64 channels, B); thread = channel pair x row lane (8 lanes)
-__global__ void se_pool_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
-                               const __nv_bfloat16* __restrict__ D, long long ldD,
-                               const float* __restrict__ scale, const float* __restrict__ shift, int act,
-                               int HW, int C, float inv, float* __restrict__ out) {
-  __shared__ float red[8][64];
-  const int lane = threadIdx.x & 31, rl = threadIdx.x >> 5;
-  const int ch = blockIdx.x * 64 + 2 * lane;
+// grid (C/64 blocks of 64 channels, B); thread = 8 channels (one 16-byte load) x row lane (32 lanes),
+// 4 rows in flight per thread; fixed-order cross-lane sum in shared memory.
+__global__ void __launch_bounds__(256) se_pool_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
+                                                      const __nv_bfloat16* __restrict__ D, long long ldD,
+                                                      const float* __restrict__ scale, const float* __restrict__ shift,
+                                                      int act, int HW, int C, float inv, float* __restrict__ out) {
+  __shared__ float red[32][65];
+  const int cgl = threadIdx.x & 7, rl = threadIdx.x >> 3;          // 8 channel groups x 32 row lanes
+  const int ch = blockIdx.x * 64 + cgl * 8;
   const int b = blockIdx.y;
-  float a0 = 0.f, a1 = 0.f;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
   if (ch < C) {
-    const float s0 = scale[ch], s1 = scale[ch + 1], h0 = shift[ch], h1 = shift[ch + 1];
+    float sc[8], sh[8];
+    load_coef8(scale, ch, C, sc, 0.f);
+    load_coef8(shift, ch, C, sh, 0.f);
     const __nv_bfloat16* xp = x + (static_cast<long long>(b) * HW) * ldx + ch;
     const __nv_bfloat16* dp = D ? D + (static_cast<long long>(b) * HW) * ldD + ch : nullptr;
-    for (int r = rl; r < HW; r += 8) {
-      const uint32_t w = *reinterpret_cast<const uint32_t*>(xp + r * ldx);
-      float v0 = act_fwd(fmaf(s0, bf16_lo(w), h0), act), v1 = act_fwd(fmaf(s1, bf16_hi(w), h1), act);
-      if (dp != nullptr) {
-        const uint32_t dw = *reinterpret_cast<const uint32_t*>(dp + r * ldD);
-        v0 *= bf16_lo(dw);
-        v1 *= bf16_hi(dw);
+    for (int r0 = rl; r0 < HW; r0 += 128) {
+      uint4 v[4], dv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int r = r0 + 32 * k;
+        v[k] = r < HW ? ldg_nc_v4(xp + static_cast<long long>(r) * ldx) : make_uint4(0, 0, 0, 0);
+        dv[k] = (dp != nullptr && r < HW) ? ldg_nc_v4(dp + static_cast<long long>(r) * ldD) : make_uint4(0, 0, 0, 0);
       }
-      a0 += v0;
-      a1 += v1;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (r0 + 32 * k < HW) {
+          const uint32_t vi[4] = {v[k].x, v[k].y, v[k].z, v[k].w}, di[4] = {dv[k].x, dv[k].y, dv[k].z, dv[k].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float lo = act_fwd(fmaf(sc[2 * e], bf16_lo(vi[e]), sh[2 * e]), act);
+            float hi = act_fwd(fmaf(sc[2 * e + 1], bf16_hi(vi[e]), sh[2 * e + 1]), act);
+            if (dp != nullptr) {
+              lo *= bf16_lo(di[e]);
+              hi *= bf16_hi(di[e]);
+            }
+            acc[2 * e] += lo;
+            acc[2 * e + 1] += hi;
+          }
+        }
+      }
     }
   }
-  red[rl][2 * lane] = a0;
-  red[rl][2 * lane + 1] = a1;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) red[rl][cgl * 8 + e] = acc[e];
   __syncthreads();
   if (threadIdx.x < 64) {
     float t = 0.f;
-#pragma unroll
-    for (int l = 0; l < 8; ++l) t += red[l][threadIdx.x];
+#pragma unroll 8
+    for (int l = 0; l < 32; ++l) t += red[l][threadIdx.x];
     const int c = blockIdx.x * 64 + threadIdx.x;
     if (c < C) out[static_cast<long long>(b) * C + c] = t * inv;
   }
@@ -147,12 +167,26 @@ __global__ void se_gate_bwd_kernel(const float* __restrict__ dgate, const float*
     }
   }
   __syncthreads();
-  for (int j = threadIdx.x; j < mid; j += blockDim.x) {
-    float t = 0.f;
-    for (int m = 0; m < total; ++m) t = fmaf(W2[static_cast<long long>(m) * mid + j], z[m], t);
-    t *= act_bwd(hpre[static_cast<long long>(b) * mid + j], act);
-    h[j] = t;
-    dh[static_cast<long long>(b) * mid + j] = t;
+  // da[j] = sum_m W2[m, j] * dz[m]: warps split m (fixed partition), lanes run along j (coalesced
+  // rows of W2); per-warp partials are combined in warp order -> deterministic
+  {
+    float* part = sm + total + mid;                // [nwarps][mid]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int j0 = 0; j0 < mid; j0 += 32) {
+      const int j = j0 + lane;
+      float t = 0.f;
+      if (j < mid)
+        for (int m = warp; m < total; m += nw) t = fmaf(W2[static_cast<long long>(m) * mid + j], z[m], t);
+      if (j < mid) part[warp * mid + j] = t;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < mid; j += blockDim.x) {
+      float t = 0.f;
+      for (int wv = 0; wv < nw; ++wv) t += part[wv * mid + j];
+      t *= act_bwd(hpre[static_cast<long long>(b) * mid + j], act);
+      h[j] = t;
+      dh[static_cast<long long>(b) * mid + j] = t;
+    }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -320,8 +354,8 @@ extern "C" int an_se_gate_bwd(const float* dgate, const float* gate, const float
                               float* dW2, float* db2, void* stream) {
   AN_REQUIRE(dgate && gate && hpre && pooled && W1 && W2 && chmap && inv_map && dz && dh && ds && dW1 && db1 && dW2 &&
                  db2, "an_se_gate_bwd: bad arguments");
-  const size_t smem = static_cast<size_t>(total + mid) * 4;
-  AN_REQUIRE(smem <= 48 * 1024, "an_se_gate_bwd: %d + %d floats of shared memory", total, mid);
+  const size_t smem = static_cast<size_t>(total + mid + 8 * mid) * 4;          // + per-warp partials of da
+  AN_REQUIRE(smem <= 48 * 1024, "an_se_gate_bwd: %d + 9 x %d floats of shared memory", total, mid);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   se_gate_bwd_kernel<<<B, 256, smem, st>>>(dgate, gate, hpre, W1, W2, chmap, act, C, total, mid, dz, dh, ds);
   AN_CHECK_LAUNCH();

@@ -478,6 +478,8 @@ class Engine(object):
             if p.branches:
                 if p.expand:
                     bb.e_raw = bf16(M, p.Kh)      # raw expand output: the depthwise kernels apply BN + act on load
+                    if p.act == 3:                # Swish: exp + rcp per loaded word is too dear on the
+                        bb.u = bf16(M, p.Kh)      # (halo-redundant) load path -> materialise act(bn(e_raw)) once
                     part_max = max(part_max, K.pw_gemm_stats_rows(M, p.Kh) * 2 * p.Kh)
                     wpart_max = max(wpart_max, K.pw_wgrad_splits(M, p.Kh, p.inp) * p.Kh * p.inp)
                     big_e = max(big_e, M * p.Kh)
@@ -656,6 +658,9 @@ class Engine(object):
             # (csrc/dw2.cu): the activated 6x-expanded tensor is never written to HBM
             src, ld_src = bb.e_raw, p.Kh
             x_scale, x_shift = self.bn_vec(p.bn_e, "scale"), self.bn_vec(p.bn_e, "shift")
+            if p.act == 3:
+                K.affine_act(bb.e_raw, bb.u, M, p.Kh, ld1=p.Kh, ldo=p.Kh, a1=x_scale, a3=x_shift, act=p.act)
+                src, x_scale, x_shift = bb.u, None, None
         else:
             src, ld_src, x_scale, x_shift = x, p.inp, None, None
         for br in p.branches:
@@ -819,10 +824,14 @@ class Engine(object):
         if p.expand:
             usrc, ld_src = bb.e_raw, p.Kh          # raw expand output; BN + act re-applied on load
             e_scale, e_shift = self.bn_vec(p.bn_e, "scale"), self.bn_vec(p.bn_e, "shift")
+            w_scale, w_shift = e_scale, e_shift    # on-load operand transform of the weight gradient
+            if p.act == 3:
+                usrc, w_scale, w_shift = bb.u, None, None
             e_mean, e_rstd = self.bn_vec(p.bn_e, "mean"), self.bn_vec(p.bn_e, "rstd")
             eraw, ge, ld_ge = bb.e_raw, bf.g_e, p.Kh
         else:
             usrc, ld_src, e_scale, e_shift, e_mean, e_rstd = bb.x, p.inp, None, None, None, None
+            w_scale, w_shift = None, None
             eraw, ge, ld_ge = bb.x, (dx if not p.res else bf.g_e), p.inp
 
         def sl(v, br):
@@ -832,11 +841,11 @@ class Engine(object):
             o = br.off
             TAG[0] = "bwd.dw%d_wgrad" % br.k
             if br.hp == br.h:
-                K.dw_bwd_weight(g_d[o:], bb.d_raw[:, o:], usrc[:, o:], None, None, None, sl(e_scale, br),
-                                sl(e_shift, br), act if p.expand else 0, wpart, G[br.wd_off:], B, bb.hin, bb.win,
+                K.dw_bwd_weight(g_d[o:], bb.d_raw[:, o:], usrc[:, o:], None, None, None, sl(w_scale, br),
+                                sl(w_shift, br), act if p.expand else 0, wpart, G[br.wd_off:], B, bb.hin, bb.win,
                                 br.hp, br.k, p.stride, ldg=p.Kh, ldd=p.Kh, lde=ld_src)
             else:
-                self._dw_wgrad_padded(p, bb, br, g_d, usrc, ld_src, B, wpart, sl(e_scale, br), sl(e_shift, br))
+                self._dw_wgrad_padded(p, bb, br, g_d, usrc, ld_src, B, wpart, sl(w_scale, br), sl(w_shift, br))
             TAG[0] = "bwd.dw%d_dgrad" % br.k
             K.dw_bwd_data(g_d[o:], bb.d_raw[:, o:], eraw[:, o:], ge[o:], self.W32[br.wd32:], None, None, None,
                           sl(e_scale, br), sl(e_shift, br), sl(e_mean, br), sl(e_rstd, br),

@@ -321,9 +321,12 @@ def block_forward_bf16_points(spec, st, b, y, training=True):
         t, d = y, 0
         if b.expand:
             t = _q2(F.conv2d(y, _qw(st[base + ".0.0.weight"])))
-            # the depthwise kernels apply BN + activation to the raw (bf16) expand output ON LOAD, in
-            # fp32: the activated operand itself is not rounded (round 2; it was a bf16 tensor before)
+            # ReLU / ReLU6 / identity: the depthwise kernels apply BN + activation to the raw (bf16)
+            # expand output ON LOAD, in fp32 -- the activated operand is not rounded.  Swish: the engine
+            # materialises act(bn(.)) as a bf16 tensor first (exp on the load path is too dear).
             t = act(_qb(_bn(spec, st, base + ".0.1", t, training)), a)
+            if a == "nn.Swish":
+                t = _qf(t)
             d = 1
         t = _q2(F.conv2d(t, st["%s.%d.0.weight" % (base, d)], None, b.stride, (k - 1) // 2, 1, h))
         t = _qf(act(_qb(_bn(spec, st, "%s.%d.1" % (base, d), t, training)), a))

@@ -85,6 +85,16 @@ BLOCKS = [
     (16, 16, 1, [32, 24, 40], [3, 5, 7], True, "nn.Swish", 8, 24),
     (24, 24, 1, [13, 51, 23], [3, 5, 7], True, "nn.ReLU", 4, 14),     # pruned widths -> padded slots
     (32, 40, 2, [96, 96], [5, 7], True, "nn.ReLU", 3, 28),
+    # the AtomNAS-C supernet's own layer shapes at 224 (BASELINE configs 2 / 3), small batch:
+    (32, 16, 1, [32], [3], False, "nn.ReLU", 2, 112),                  # features.1
+    (16, 24, 2, [96, 96, 96], [3, 5, 7], True, "nn.ReLU", 2, 112),     # features.2
+    (24, 24, 1, [144, 144, 144], [3, 5, 7], True, "nn.ReLU", 2, 56),   # features.3-5 (tail channel block)
+    (24, 40, 2, [144, 144, 144], [3, 5, 7], True, "nn.ReLU", 3, 56),   # features.6
+    (40, 40, 1, [240, 240, 240], [3, 5, 7], True, "nn.ReLU", 3, 28),   # features.7-9
+    (80, 96, 1, [480, 480, 480], [3, 5, 7], True, "nn.ReLU", 4, 14),   # features.14
+    (96, 192, 2, [576, 576, 576], [3, 5, 7], True, "nn.ReLU", 5, 14),  # features.18
+    (192, 320, 1, [1152, 1152, 1152], [3, 5, 7], True, "nn.ReLU", 6, 7),   # features.22
+    (24, 24, 1, [20, 3, 2], [3, 5, 7], True, "nn.ReLU", 3, 56),        # searched AtomNAS-C widths (features.3)
 ]
 
 
