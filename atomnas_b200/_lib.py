@@ -56,6 +56,14 @@ class DwBwdArgs(ctypes.Structure):
     ]
 
 
+class BnSeg(ctypes.Structure):
+    _fields_ = [("part", c_fp), ("rows", c_int), ("c0", c_int), ("C", c_int)]
+
+
+class WgSeg(ctypes.Structure):
+    _fields_ = [("row0", c_int), ("nrows", c_int), ("dst", c_fp), ("dst_sb", c_ll), ("dst_ss", c_ll)]
+
+
 c_f, c_d, c_ull = ctypes.c_float, ctypes.c_double, ctypes.c_ulonglong
 
 # name -> (restype, argtypes); must list every symbol of include/atomnas_b200.h
@@ -107,6 +115,11 @@ SIGNATURES = {
     "an_reg_losses": (c_int, [c_fp, c_fp, c_fp, c_ll, c_fp, c_vp]),
     "an_refresh_weights": (c_int, [c_vp, c_int, c_ll, c_fp, c_vp, c_fp, c_vp]),
     "an_gather_rows": (c_int, [c_fp, c_vp, c_ll, c_ll, c_fp, c_vp]),
+    "an_bn_finalize_multi": (c_int, [ctypes.POINTER(BnSeg), c_int, c_d, c_fp, c_fp, c_fp, c_fp, c_f, c_f, c_fp, c_fp,
+                                     c_fp, c_fp, c_vp]),
+    "an_bn_bwd_finalize_multi": (c_int, [ctypes.POINTER(BnSeg), c_int, c_d, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp,
+                                         c_fp, c_int, c_vp]),
+    "an_wgrad_reduce_multi": (c_int, [c_fp, c_int, c_int, c_int, c_int, ctypes.POINTER(WgSeg), c_int, c_vp]),
     "an_se_pool": (c_int, [c_vp, c_ll, c_vp, c_ll, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_fp, c_vp]),
     "an_se_gate": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_vp, c_int, c_int, c_int, c_int, c_int, c_fp, c_fp, c_vp]),
     "an_se_scale": (c_int, [c_vp, c_ll, c_fp, c_fp, c_int, c_fp, c_int, c_int, c_int, c_vp, c_ll, c_vp]),

@@ -90,6 +90,89 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int rows,
   cc[c] = -a * static_cast<float>(s1 / count) - b * mean[c];
 }
 
+// Several independent partial buffers finalised by ONE launch: the three depthwise branches of a
+// block write their statistics with different partial-row counts; segment s covers channels
+// [c0, c0 + C) of the branch-fused BatchNorm vectors.  blockIdx.y = segment.
+struct BnSegs {
+  const float* part[4];
+  int rows[4], c0[4], C[4];
+};
+
+__device__ __forceinline__ bool reduce_partials_seg(const float* __restrict__ part, int rows, int C, double* s1,
+                                                    double* s2, int* c_out) {
+  __shared__ double sh[2][kFinLanes][32];
+  const int lc = threadIdx.x % 32, lr = threadIdx.x / 32;
+  const int c = blockIdx.x * 32 + lc;
+  double a = 0.0, b = 0.0;
+  if (c < C) {
+    for (int r = lr; r < rows; r += kFinLanes) {
+      a += static_cast<double>(part[(static_cast<long long>(r) * 2 + 0) * C + c]);
+      b += static_cast<double>(part[(static_cast<long long>(r) * 2 + 1) * C + c]);
+    }
+  }
+  sh[0][lr][lc] = a;
+  sh[1][lr][lc] = b;
+  __syncthreads();
+  if (lr != 0 || c >= C) return false;
+  a = 0.0;
+  b = 0.0;
+  for (int l = 0; l < kFinLanes; ++l) {
+    a += sh[0][l][lc];
+    b += sh[1][l][lc];
+  }
+  *s1 = a;
+  *s2 = b;
+  *c_out = c;
+  return true;
+}
+
+__global__ void bn_finalize_multi_kernel(const __grid_constant__ BnSegs sg, double count,
+                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                         float* running_mean, float* running_var, float momentum, float eps,
+                                         float* mean_out, float* rstd_out, float* scale_out, float* shift_out) {
+  const int s = blockIdx.y;
+  double s1, s2;
+  int cl;
+  if (!reduce_partials_seg(sg.part[s], sg.rows[s], sg.C[s], &s1, &s2, &cl)) return;
+  const int c = sg.c0[s] + cl;
+  const double mean = s1 / count;
+  double var = s2 / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  const float fm = static_cast<float>(mean);
+  mean_out[c] = fm;
+  rstd_out[c] = rstd;
+  const float sc = g * rstd;
+  scale_out[c] = sc;
+  shift_out[c] = b - fm * sc;
+  if (running_mean != nullptr) {
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * fm;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
+  }
+}
+
+__global__ void bn_bwd_finalize_multi_kernel(const __grid_constant__ BnSegs sg, double count,
+                                             const float* __restrict__ gamma, const float* __restrict__ mean,
+                                             const float* __restrict__ rstd, float* dgamma, float* dbeta, float* ca,
+                                             float* cb, float* cc, int raw_second) {
+  const int s = blockIdx.y;
+  double s1, s2;
+  int cl;
+  if (!reduce_partials_seg(sg.part[s], sg.rows[s], sg.C[s], &s1, &s2, &cl)) return;
+  const int c = sg.c0[s] + cl;
+  if (raw_second) s2 = static_cast<double>(rstd[c]) * (s2 - static_cast<double>(mean[c]) * s1);
+  if (dbeta) dbeta[c] = static_cast<float>(s1);
+  if (dgamma) dgamma[c] = static_cast<float>(s2);
+  const float g = gamma ? gamma[c] : 1.f;
+  const float a = g * rstd[c];
+  const float b = -a * rstd[c] * static_cast<float>(s2 / count);
+  ca[c] = a;
+  cb[c] = b;
+  cc[c] = -a * static_cast<float>(s1 / count) - b * mean[c];
+}
+
 // out = act(a1[c]*x1 + a2[c]*x2 + a3[c]); a1/a2 default 1, a3 default 0, x2 optional.
 // A thread owns ONE 8-channel group (its coefficients stay in registers) and walks rows with a
 // stride; 4 rows are in flight per thread (loads issued before the first use).
@@ -323,6 +406,46 @@ extern "C" int an_bn_bwd_finalize(const float* stats_part, int rows, int C, doub
   AN_REQUIRE(stats_part && rows > 0 && C > 0 && mean && rstd && ca && cb && cc, "an_bn_bwd_finalize: bad arguments");
   bn_bwd_finalize_kernel<<<(C + 31) / 32, 32 * kFinLanes, 0, static_cast<cudaStream_t>(stream)>>>(
       stats_part, rows, C, count, gamma, mean, rstd, dgamma, dbeta, ca, cb, cc, raw_second);
+  AN_CHECK_LAUNCH();
+  return 0;
+}
+
+static int fill_segs(BnSegs& sg, const an_bn_seg* segs, int nseg, int* cmax) {
+  AN_REQUIRE(segs != nullptr && nseg >= 1 && nseg <= 4, "bn finalize: 1..4 segments");
+  *cmax = 0;
+  for (int i = 0; i < 4; ++i) {
+    const an_bn_seg& q = segs[i < nseg ? i : 0];
+    AN_REQUIRE(q.part != nullptr && q.rows > 0 && q.C > 0 && q.c0 >= 0, "bn finalize: bad segment %d", i);
+    sg.part[i] = q.part; sg.rows[i] = q.rows; sg.c0[i] = q.c0; sg.C[i] = q.C;
+    if (i < nseg && q.C > *cmax) *cmax = q.C;
+  }
+  return 0;
+}
+
+extern "C" int an_bn_finalize_multi(const an_bn_seg* segs, int nseg, double count, const float* gamma,
+                                    const float* beta, float* running_mean, float* running_var, float momentum,
+                                    float eps, float* mean, float* rstd, float* scale, float* shift, void* stream) {
+  AN_REQUIRE(mean && rstd && scale && shift, "an_bn_finalize_multi: bad arguments");
+  BnSegs sg;
+  int cmax;
+  if (int e = fill_segs(sg, segs, nseg, &cmax)) return e;
+  dim3 grid((cmax + 31) / 32, nseg);
+  bn_finalize_multi_kernel<<<grid, 32 * kFinLanes, 0, static_cast<cudaStream_t>(stream)>>>(
+      sg, count, gamma, beta, running_mean, running_var, momentum, eps, mean, rstd, scale, shift);
+  AN_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int an_bn_bwd_finalize_multi(const an_bn_seg* segs, int nseg, double count, const float* gamma,
+                                        const float* mean, const float* rstd, float* dgamma, float* dbeta, float* ca,
+                                        float* cb, float* cc, int raw_second, void* stream) {
+  AN_REQUIRE(mean && rstd && ca && cb && cc, "an_bn_bwd_finalize_multi: bad arguments");
+  BnSegs sg;
+  int cmax;
+  if (int e = fill_segs(sg, segs, nseg, &cmax)) return e;
+  dim3 grid((cmax + 31) / 32, nseg);
+  bn_bwd_finalize_multi_kernel<<<grid, 32 * kFinLanes, 0, static_cast<cudaStream_t>(stream)>>>(
+      sg, count, gamma, mean, rstd, dgamma, dbeta, ca, cb, cc, raw_second);
   AN_CHECK_LAUNCH();
   return 0;
 }

@@ -15,6 +15,8 @@
 // tcgen05.mma issuer, warps 2-5 = operand prologue (in-place transform of the 128B-swizzled
 // tile), warps 6-9 = epilogue (tcgen05.ld -> registers -> global).  mbarrier pipelines:
 // full/xf/empty per smem stage, tfull/tempty per TMEM accumulator buffer.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "../../include/atomnas_b200.h"
 
@@ -32,6 +34,7 @@ constexpr int kTmemCols = 512;             // 2 x 128 accumulator columns + 128 
 constexpr int kTmemStat1 = 256;            // D1 = Y^T Y (or G^T R): the diagonal holds the second moments
 constexpr int kTmemStat2 = 384;            // D2 = Y^T 1: column sums
 constexpr int kGroupBytes = kBM * 128;     // one staged 64-column group of an output tile: 128 rows x 128 B
+constexpr int kMaxStaging = 4;            // staged output (and operand) tiles a CTA may keep in flight
 constexpr int kBarBytes = 384;
 constexpr int kAuxBytes = kBarBytes + 4 * 2 * kMaxBN * 4 + 2 * kMaxGroupCols * 4 + kMaxBN * 8;
 
@@ -93,11 +96,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pw_gemm_kernel(const __grid_c
   uint64_t* tfull = empty + 8;
   uint64_t* tempty = tfull + 2;
   uint64_t* sfull = tempty + 2;
-  uint64_t* rfull = sfull + 1;
-  uint64_t* rempty = rfull + 2;
-  uint64_t* yfull = rempty + 2;            // staged output tile written by every epilogue thread
-  uint64_t* yempty = yfull + 2;            // ... and free again (its TMA store has read it)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(yempty + 2);
+  uint64_t* rfull = sfull + 1;             // up to kMaxStaging staged tiles in flight (p.nbuf)
+  uint64_t* rempty = rfull + kMaxStaging;
+  uint64_t* yfull = rempty + kMaxStaging;  // staged output tile written by every epilogue thread
+  uint64_t* yempty = yfull + kMaxStaging;  // ... and free again (its TMA store has read it)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(yempty + kMaxStaging);
   float* stat_warp = reinterpret_cast<float*>(aux + kBarBytes);   // [4][2][kMaxBN] (direct epilogue only)
   float* stat_acc = stat_warp + 4 * 2 * kMaxBN;                   // [2][kMaxGroupCols]
   float2* colpar = reinterpret_cast<float2*>(stat_acc + 2 * kMaxGroupCols);   // [kMaxBN]
@@ -120,6 +123,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pw_gemm_kernel(const __grid_c
       for (int b = 0; b < 2; ++b) {
         mbar_init(&tfull[b], 1);
         mbar_init(&tempty[b], p.a_mode == 0 ? 8 : 4);   // one elected arrival per epilogue warp
+      }
+      for (int b = 0; b < kMaxStaging; ++b) {
         mbar_init(&rfull[b], 1);
         mbar_init(&rempty[b], 1);
         mbar_init(&yfull[b], p.a_mode == 0 ? 8 : 4);
@@ -209,13 +214,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pw_gemm_kernel(const __grid_c
           } else if (has_r) {
             mbar_arrive(&rempty[yb]);                       // every epilogue thread is past its reads
           }
-          if (p.nbuf == 2) {
-            tma_store_wait_read<1>();                       // store of the previous tile has read its smem
-            if (tc > 0) mbar_arrive(&yempty[yb ^ 1]);
-          } else {
-            tma_store_wait_read<0>();
-            mbar_arrive(&yempty[0]);
+          // keep nbuf - 1 stores in flight: the store issued nbuf - 1 tiles ago has read its smem.
+          // (HBM write latency x bandwidth needs > 64 KB in flight per SM: 2 staging tiles cap a
+          // store-bound GEMM at ~40 % of the HBM roof, 4 tiles lift that)
+          switch (p.nbuf) {
+            case 4: tma_store_wait_read<3>(); break;
+            case 3: tma_store_wait_read<2>(); break;
+            case 2: tma_store_wait_read<1>(); break;
+            default: tma_store_wait_read<0>(); break;
           }
+          if (tc + 1 >= static_cast<uint32_t>(p.nbuf)) mbar_arrive(&yempty[(tc + 1 - p.nbuf) % p.nbuf]);
         }
       tma_store_wait<0>();
     }
@@ -730,6 +738,44 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partials, int spli
   }
 }
 
+// The same reduction for up to 4 row ranges of ONE partial buffer in one launch (the branch-fused
+// weight gradient is un-fused into the per-branch master tensors): blockIdx.y = range.
+struct WgSegs {
+  int row0[4], nrows[4];
+  float* dst[4];
+  long long sb[4], ss[4];
+};
+__global__ void wgrad_reduce_multi_kernel(const float* __restrict__ partials, int splits, int Cbig, int Csmall,
+                                          int ncols, const __grid_constant__ WgSegs sg) {
+  __shared__ float red[8][33];
+  const int q = blockIdx.y;
+  const int row0 = sg.row0[q], nrows = sg.nrows[q];
+  float* __restrict__ dst = sg.dst[q];
+  const long long sb = sg.sb[q], ss = sg.ss[q];
+  const long long full = static_cast<long long>(Cbig) * Csmall;
+  const long long n = static_cast<long long>(nrows) * ncols;
+  const int ex = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  for (long long base = blockIdx.x * 32LL; base < n; base += gridDim.x * 32LL) {
+    const long long i = base + ex;
+    float acc = 0.f;
+    long long cb = 0, cs = 0;
+    if (i < n) {
+      cb = i / ncols; cs = i % ncols;
+      const long long src = (row0 + cb) * Csmall + cs;
+      for (int s = sl; s < splits; s += 8) acc += partials[s * full + src];
+    }
+    red[sl][ex] = acc;
+    __syncthreads();
+    if (sl == 0 && i < n) {
+      float a = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a += red[k][ex];
+      dst[cb * sb + cs * ss] = a;
+    }
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -805,8 +851,19 @@ extern "C" int an_pw_gemm(const an_pw_gemm_args* a, void* stream) {
   const int stage_bytes = a_bytes + kTileB;
   d.staged = (!a->y_is_f32 && a->bias == nullptr) ? 1 : 0;
   const bool has_r = d.staged && a->r != nullptr && a->epi_mode != 0;
-  d.nbuf = (a->a_mode == 2) ? 1 : 2;
   d.ytile_bytes = (g.block_n / 64) * kGroupBytes;
+  // staged tiles in flight: as many as shared memory allows next to >= min(3, k-blocks + 1) operand stages
+  {
+    const int kblocks = (a->K + kBK - 1) / kBK;
+    const int want_stages = kblocks + 1 < 3 ? kblocks + 1 : 3;
+    const int per_buf = d.ytile_bytes * ((d.staged && a->r != nullptr && a->epi_mode != 0) ? 2 : 1);
+    const int avail = 227 * 1024 - 1024 - kAuxBytes - kGroupBytes - want_stages * stage_bytes;
+    int nb = d.staged ? avail / per_buf : 2;
+    if (nb > kMaxStaging) nb = kMaxStaging;
+    if (nb < 1) nb = 1;
+    if (getenv("AN_PW_NBUF") != nullptr) { const int e = atoi(getenv("AN_PW_NBUF")); if (e >= 1 && e < nb) nb = e; }
+    d.nbuf = nb;
+  }
   int fixed = 0;
   if (d.staged) {
     if (int e = make_tmap_bf16_2d(&d.tm_y, a->y, a->N, a->M, a->ldy, 64, kBM)) return e;
@@ -915,6 +972,26 @@ extern "C" int an_wgrad_reduce(const float* partials, int splits, int Cbig, int 
   int blocks = static_cast<int>((n + 31) / 32);
   if (blocks > 16 * sm_count()) blocks = 16 * sm_count();
   wgrad_reduce_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(partials, splits, Cbig, Csmall, row0, nrows, ncols, dst, dst_sb, dst_ss);
+  AN_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int an_wgrad_reduce_multi(const float* partials, int splits, int Cbig, int Csmall, int ncols,
+                                     const an_wg_seg* segs, int nseg, void* stream) {
+  AN_REQUIRE(partials && segs && splits > 0 && nseg >= 1 && nseg <= 4 && ncols > 0 && ncols <= Csmall,
+             "an_wgrad_reduce_multi: bad arguments");
+  WgSegs sg;
+  long long nmax = 0;
+  for (int i = 0; i < 4; ++i) {
+    const an_wg_seg& q = segs[i < nseg ? i : 0];
+    AN_REQUIRE(q.dst != nullptr && q.row0 >= 0 && q.nrows > 0 && q.row0 + q.nrows <= Cbig, "an_wgrad_reduce_multi: bad segment %d", i);
+    sg.row0[i] = q.row0; sg.nrows[i] = q.nrows; sg.dst[i] = q.dst; sg.sb[i] = q.dst_sb; sg.ss[i] = q.dst_ss;
+    if (i < nseg && static_cast<long long>(q.nrows) * ncols > nmax) nmax = static_cast<long long>(q.nrows) * ncols;
+  }
+  int blocks = static_cast<int>((nmax + 31) / 32);
+  if (blocks > 8 * sm_count()) blocks = 8 * sm_count();
+  dim3 grid(blocks, nseg);
+  wgrad_reduce_multi_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(partials, splits, Cbig, Csmall, ncols, sg);
   AN_CHECK_LAUNCH();
   return 0;
 }

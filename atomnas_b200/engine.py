@@ -500,9 +500,11 @@ class Engine(object):
                     bb.vg = bf16(Mo, p.Kh)           # act(bn(d_raw)) * gate: the projection's A operand
                     se_max = max(se_max, B * max(p.Kh, q.total))
                     part_max = max(part_max, K.se_bwd_apply_rows(Mo, p.Kh) * 2 * p.Kh)
+                # each branch keeps its own region of `part` (one multi-segment finalize per block)
+                pf = sum(K.dw_fwd_stats_rows(B, br.hp, ho, wo, br.k, p.stride, False) * 2 * br.hp + 8 for br in p.branches)
+                pb = sum(K.dw_bwd_data_stats_rows(B, br.hp, h, w, br.k, p.stride, False) * 2 * br.hp + 8 for br in p.branches)
+                part_max = max(part_max, pf, pb)
                 for br in p.branches:
-                    part_max = max(part_max, K.dw_fwd_stats_rows(B, br.hp, ho, wo, br.k, p.stride, False) * 2 * br.hp,
-                                   K.dw_bwd_data_stats_rows(B, br.hp, h, w, br.k, p.stride, False) * 2 * br.hp)
                     wpart_max = max(wpart_max, K.dw_bwd_weight_rows(B, br.hp, h, w, br.k, p.stride, False) * br.k * br.k * br.hp)
                 part_max = max(part_max, K.pw_gemm_stats_rows(Mo, p.oup) * 2 * p.oup,
                                K.pw_gemm_stats_rows(Mo, p.Kh) * 2 * p.Kh,
@@ -560,6 +562,22 @@ class Engine(object):
         else:
             K.bn_eval_coeffs(self.gamma(g)[sl], self.beta(g)[sl], self.rmean(g)[sl], self.rvar(g)[sl],
                              g.eps, C, scale, shift)
+
+    def _bn_fwd_multi(self, g, segs, count, training):
+        """One launch for the whole (branch-fused) group; segs = [(part view, rows, c0, C)] per branch."""
+        if not training:
+            K.bn_eval_coeffs(self.gamma(g), self.beta(g), self.rmean(g), self.rvar(g), g.eps, g.C,
+                             self.bn_vec(g, "scale"), self.bn_vec(g, "shift"))
+            return
+        K.bn_finalize_multi(segs, count, self.gamma(g), self.beta(g), self.rmean(g), self.rvar(g), g.mom_now, g.eps,
+                            self.bn_vec(g, "mean"), self.bn_vec(g, "rstd"), self.bn_vec(g, "scale"),
+                            self.bn_vec(g, "shift"))
+        g.count = count
+
+    def _bn_bwd_multi(self, g, segs, raw_second=False):
+        K.bn_bwd_finalize_multi(segs, g.count, self.gamma(g), self.bn_vec(g, "mean"), self.bn_vec(g, "rstd"),
+                                self.dgamma(g), self.dbeta(g), self.bn_vec(g, "ca"), self.bn_vec(g, "cb"),
+                                self.bn_vec(g, "cc"), raw_second=raw_second)
 
     def _bn_bwd(self, g, part, rows, C=None, off=0, raw_second=False):
         C = g.C if C is None else C
@@ -663,14 +681,18 @@ class Engine(object):
                 src, x_scale, x_shift = bb.u, None, None
         else:
             src, ld_src, x_scale, x_shift = x, p.inp, None, None
+        segs, poff = [], 0
         for br in p.branches:
             TAG[0] = "fwd.dw%d" % br.k
+            rows = K.dw_fwd_stats_rows(B, br.hp, bb.ho, bb.wo, br.k, p.stride, False)
+            pbr = part[poff:] if training else None
             K.dw_fwd(src[:, br.off:], bb.d_raw[:, br.off:], self.W32[br.wd32:], B, bb.hin, bb.win, br.hp,
-                     br.k, p.stride, ldx=ld_src, ldy=p.Kh, act=p.act if p.expand else 0, stats_part=stats,
+                     br.k, p.stride, ldx=ld_src, ldy=p.Kh, act=p.act if p.expand else 0, stats_part=pbr,
                      scale=None if x_scale is None else x_scale[br.off:],
                      shift=None if x_shift is None else x_shift[br.off:])
-            self._bn_fwd(p.bn_d, part, K.dw_fwd_stats_rows(B, br.hp, bb.ho, bb.wo, br.k, p.stride, False), Mo,
-                         training, C=br.hp, off=br.off)
+            segs.append((pbr, rows, br.off, br.hp))
+            poff += rows * 2 * br.hp + 8
+        self._bn_fwd_multi(p.bn_d, segs, Mo, training)
         if p.se is not None:
             # squeeze-and-excitation on the activated depthwise output (mobilenet_base.py:93-117):
             # pooled mean -> two tiny FCs -> sigmoid gate -> vg = v * gate feeds the projection
@@ -787,8 +809,8 @@ class Engine(object):
             # project weight gradient: dWp[oup, h_i] = dp^T act(bn(d_raw))
             TAG[0] = "bwd.project_wgrad"
             sp = K.pw_wgrad(bb.d_raw, dp, wpart, Mo, p.Kh, p.oup, p_mode=1, p_act=act, a1=d_scale, a3=d_shift)
-            for br in p.branches:
-                K.wgrad_reduce(wpart, sp, p.Kh, p.oup, G[br.wp_off:], 1, br.wp_ss, row0=br.off, nrows=br.h)
+            K.wgrad_reduce_multi(wpart, sp, p.Kh, p.oup, p.oup,
+                                 [(br.off, br.h, G[br.wp_off:], 1, br.wp_ss) for br in p.branches])
             # project data gradient with act/BN backward epilogue -> g_d
             TAG[0] = "bwd.project_dgrad"
             K.pw_gemm(dp, self.W16[p.wpT16:], g_d, Mo, p.Kh, p.oup, epi_mode=1, r=bb.d_raw, ldr=p.Kh,
@@ -804,8 +826,8 @@ class Engine(object):
             HW = Mo // B
             TAG[0] = "bwd.project_wgrad"
             sp = K.pw_wgrad(bb.vg, dp, wpart, Mo, p.Kh, p.oup)
-            for br in p.branches:
-                K.wgrad_reduce(wpart, sp, p.Kh, p.oup, G[br.wp_off:], 1, br.wp_ss, row0=br.off, nrows=br.h)
+            K.wgrad_reduce_multi(wpart, sp, p.Kh, p.oup, p.oup,
+                                 [(br.off, br.h, G[br.wp_off:], 1, br.wp_ss) for br in p.branches])
             TAG[0] = "bwd.project_dgrad"
             K.pw_gemm(dp, self.W16[p.wpT16:], g_d, Mo, p.Kh, p.oup)
             TAG[0] = "bwd.se"
@@ -837,6 +859,7 @@ class Engine(object):
         def sl(v, br):
             return None if v is None else v[br.off:]
 
+        segs, poff = [], 0
         for br in p.branches:
             o = br.off
             TAG[0] = "bwd.dw%d_wgrad" % br.k
@@ -849,12 +872,14 @@ class Engine(object):
             TAG[0] = "bwd.dw%d_dgrad" % br.k
             K.dw_bwd_data(g_d[o:], bb.d_raw[:, o:], eraw[:, o:], ge[o:], self.W32[br.wd32:], None, None, None,
                           sl(e_scale, br), sl(e_shift, br), sl(e_mean, br), sl(e_rstd, br),
-                          part if p.expand else None, act if p.expand else 0, B, bb.hin, bb.win, br.hp, br.k,
-                          p.stride, ldg=p.Kh, ldd=p.Kh, lde=ld_src, ldge=ld_ge)
+                          part[poff:] if p.expand else None, act if p.expand else 0, B, bb.hin, bb.win, br.hp,
+                          br.k, p.stride, ldg=p.Kh, ldd=p.Kh, lde=ld_src, ldge=ld_ge)
             if p.expand:
-                self._bn_bwd(p.bn_e, part,
-                             K.dw_bwd_data_stats_rows(B, br.hp, bb.hin, bb.win, br.k, p.stride, False),
-                             C=br.hp, off=o)
+                rows = K.dw_bwd_data_stats_rows(B, br.hp, bb.hin, bb.win, br.k, p.stride, False)
+                segs.append((part[poff:], rows, o, br.hp))
+                poff += rows * 2 * br.hp + 8
+        if p.expand:
+            self._bn_bwd_multi(p.bn_e, segs)
         if not p.expand:
             if p.res:
                 K.affine_act(ge, dx, M, p.inp, ld1=p.inp, ldo=p.inp, x2=dy, ld2=p.oup)
@@ -862,8 +887,8 @@ class Engine(object):
         eca, ecb, ecc = (self.bn_vec(p.bn_e, n) for n in ("ca", "cb", "cc"))
         TAG[0] = "bwd.expand_wgrad"
         sp = K.pw_wgrad(ge, bb.x, wpart, M, p.Kh, p.inp, p2=bb.e_raw, p_mode=2, a1=eca, a2=ecb, a3=ecc)
-        for br in p.branches:
-            K.wgrad_reduce(wpart, sp, p.Kh, p.inp, G[br.we_off:], p.inp, 1, row0=br.off, nrows=br.h)
+        K.wgrad_reduce_multi(wpart, sp, p.Kh, p.inp, p.inp,
+                             [(br.off, br.h, G[br.we_off:], p.inp, 1) for br in p.branches])
         TAG[0] = "bwd.expand_dgrad"
         K.pw_gemm(ge, self.W16[p.weT16:], dx, M, p.inp, p.Kh, x2=bb.e_raw, a_mode=2, a1=eca, a2=ecb, a3=ecc,
                   epi_mode=2, r=dy if p.res else None, ldr=p.oup)

@@ -278,3 +278,35 @@ def se_bwd_apply(D, ldD, x, ldx, scale, shift, mean, rstd, act, gate, ds, B, HW,
     L.check(L.lib().an_se_bwd_apply(_c(D), ldD, _c(x), ldx, _c(scale), _c(shift), _c(mean), _c(rstd), act,
                                     _c(gate), _c(ds), B, HW, C, _c(g), ldg, _c(part), L.stream_ptr()),
             "an_se_bwd_apply")
+
+
+# ------------------------------------------------------------------------------------------------
+# multi-segment variants (one launch for the three branches of a block)
+# ------------------------------------------------------------------------------------------------
+def _bn_segs(segs):
+    """segs: [(part tensor, rows, c0, C)]"""
+    arr = (L.BnSeg * 4)()
+    for i, (part, rows, c0, C) in enumerate(segs):
+        arr[i].part, arr[i].rows, arr[i].c0, arr[i].C = _c(part), rows, c0, C
+    return arr
+
+
+def bn_finalize_multi(segs, count, gamma, beta, rm, rv, momentum, eps, mean, rstd, scale, shift):
+    L.check(L.lib().an_bn_finalize_multi(_bn_segs(segs), len(segs), float(count), _c(gamma), _c(beta), _c(rm),
+                                         _c(rv), momentum, eps, _c(mean), _c(rstd), _c(scale), _c(shift),
+                                         L.stream_ptr()), "an_bn_finalize_multi")
+
+
+def bn_bwd_finalize_multi(segs, count, gamma, mean, rstd, dgamma, dbeta, ca, cb, cc, raw_second=False):
+    L.check(L.lib().an_bn_bwd_finalize_multi(_bn_segs(segs), len(segs), float(count), _c(gamma), _c(mean),
+                                             _c(rstd), _c(dgamma), _c(dbeta), _c(ca), _c(cb), _c(cc),
+                                             1 if raw_second else 0, L.stream_ptr()), "an_bn_bwd_finalize_multi")
+
+
+def wgrad_reduce_multi(partials, splits, Cbig, Csmall, ncols, segs):
+    """segs: [(row0, nrows, dst tensor view, sb, ss)]"""
+    arr = (L.WgSeg * 4)()
+    for i, (row0, nrows, dst, sb, ss) in enumerate(segs):
+        arr[i].row0, arr[i].nrows, arr[i].dst, arr[i].dst_sb, arr[i].dst_ss = row0, nrows, _c(dst), sb, ss
+    L.check(L.lib().an_wgrad_reduce_multi(_c(partials), splits, Cbig, Csmall, ncols, arr, len(segs),
+                                          L.stream_ptr()), "an_wgrad_reduce_multi")

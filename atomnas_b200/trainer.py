@@ -14,9 +14,10 @@ the same engine through atomnas_b200.rmsprop / atomnas_b200.optim instead.
 
 CUDA graphs.  One rank: the whole step is one graph.  Several ranks: the step is two graphs
 (forward + backward, optimizer) around ONE in-place NCCL all-reduce of the gradient arena issued
-from Python (45 MB over NVSwitch is ~0.2 ms against a >30 ms step, so overlapping it buys < 1 %;
-AN_GRAPH_NCCL=1 captures the bucketed, backward-overlapped all-reduce inside a single graph
-instead).  Eager mode (use_cuda_graph=False) keeps the bucketed overlap.
+from Python (45 MB over NVSwitch is ~0.2 ms against a >30 ms step, so overlapping it buys < 1 %:
+measured 53.8 ms/step on 2 GPUs vs 53.5 on one).  Capturing the NCCL all-reduce INSIDE the graph was
+tried and hangs with torch 2.11 / NCCL 2.28 async process groups (tests/test_multirank_gpu.py,
+round 2), so it is not offered.  Eager mode (use_cuda_graph=False) keeps the bucketed overlap.
 """
 import os
 import time
@@ -62,7 +63,6 @@ class Trainer(object):
         self.rank = dist.get_rank() if self.world > 1 else 0
         self.bucket_elems = max(1, bucket_bytes // 4)
         self.use_cuda_graph = use_cuda_graph
-        self.graph_nccl = os.environ.get("AN_GRAPH_NCCL", "0") == "1"
         self._bind(E.get_engine(model))
         self.sq = torch.zeros_like(self.eng.P)
         self.buf = torch.zeros_like(self.eng.P)
@@ -187,7 +187,7 @@ class Trainer(object):
     def _step_graphed(self, x, target):
         """Step replayed from CUDA graphs (the ~900 launches of a step are launch-bound from
         Python); lr / rho / EMA decay / dropout seed are read from device memory."""
-        split = self.world > 1 and not self.graph_nccl
+        split = self.world > 1
         if self._static is None or self._static[2] != tuple(x.shape) or self._static[4] != split:
             return self._capture(x, target, split)
         sx, sy, _, out, _ = self._static

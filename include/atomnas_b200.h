@@ -99,6 +99,10 @@ int an_pw_wgrad(const an_pw_wgrad_args* args, void* stream);
 /* dst[(cb-row0)*dst_sb + cs*dst_ss] = sum_s partials[s][cb][cs], cb in [row0,row0+nrows), cs < ncols */
 int an_wgrad_reduce(const float* partials, int splits, int Cbig, int Csmall, int row0, int nrows,
                     int ncols, float* dst, long long dst_sb, long long dst_ss, void* stream);
+/* up to 4 row ranges [row0, row0+nrows) of one partial buffer, each to its own destination, in ONE launch */
+typedef struct { int row0; int nrows; float* dst; long long dst_sb; long long dst_ss; } an_wg_seg;
+int an_wgrad_reduce_multi(const float* partials, int splits, int Cbig, int Csmall, int ncols,
+                          const an_wg_seg* segs, int nseg, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Depthwise k x k convolution (k = 3, 5, 7; stride 1, 2; pad (k-1)/2), NHWC bf16, CUDA cores.
@@ -165,6 +169,18 @@ int an_bn_finalize(const float* stats_part, int rows, int C, double count, const
 int an_bn_bwd_finalize(const float* stats_part, int rows, int C, double count, const float* gamma,
                        const float* mean, const float* rstd, float* dgamma, float* dbeta, float* ca,
                        float* cb, float* cc, int raw_second, void* stream);
+
+/* The same two finalizes for up to 4 independent partial buffers in ONE launch (the three depthwise
+ * branches of a block reduce their statistics with different partial-row counts): segment s holds
+ * [rows][2][C] partials of channels [c0, c0 + C) of the vectors passed (gamma ... shift are the
+ * branch-fused vectors' base pointers). */
+typedef struct { const float* part; int rows; int c0; int C; } an_bn_seg;
+int an_bn_finalize_multi(const an_bn_seg* segs, int nseg, double count, const float* gamma,
+                         const float* beta, float* running_mean, float* running_var, float momentum,
+                         float eps, float* mean, float* rstd, float* scale, float* shift, void* stream);
+int an_bn_bwd_finalize_multi(const an_bn_seg* segs, int nseg, double count, const float* gamma,
+                             const float* mean, const float* rstd, float* dgamma, float* dbeta, float* ca,
+                             float* cb, float* cc, int raw_second, void* stream);
 int an_affine_act(const void* x1, long long ld1, const void* x2, long long ld2, const float* a1,
                   const float* a2, const float* a3, int act, void* out, long long ldo, long long M,
                   int C, void* stream);

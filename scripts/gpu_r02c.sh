@@ -5,7 +5,7 @@ cd "${GRAFT_REPO_ROOT:-.}"
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name --format=csv > gpurun_out/${tag}_gpus.txt
 echo "== multirank pytest"
-AN_TEST_GRAPH_NCCL=1 timeout 900 python -m pytest tests/test_multirank_gpu.py -m gpu -q --timeout 400 -p no:cacheprovider > gpurun_out/${tag}_pytest_multirank.log 2>&1
+timeout 600 python -m pytest tests/test_multirank_gpu.py -m gpu -q --timeout 400 -p no:cacheprovider > gpurun_out/${tag}_pytest_multirank.log 2>&1
 tail -12 gpurun_out/${tag}_pytest_multirank.log
 for n in $(seq 2 2 $N) ; do
   [ $n -eq 6 ] && continue

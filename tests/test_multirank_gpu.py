@@ -1,8 +1,8 @@
 """Two-rank NCCL parity of the data-parallel step (utils/distributed.py:131-161,
 train.py:184-185).  Needs >= 2 GPUs (`gpurun --gpus 2`); skipped on a single-GPU box.
 
-Checks, for the eager (bucketed, backward-overlapped all-reduce), the split-graph and -- when
-AN_TEST_GRAPH_NCCL=1 -- the single-graph-with-captured-NCCL modes:
+Checks, for the eager (bucketed, backward-overlapped all-reduce) and the split-graph modes (a single
+graph with the NCCL all-reduce captured inside was tried in round 2 and hangs; it is not offered):
   * after the all-reduce the gradient arena is BIT-EQUAL on both ranks, and so are the parameters
     after the optimizer step;
   * the 2-rank step equals the 1-rank step over the same global batch with per-GPU BatchNorm
@@ -33,8 +33,6 @@ def _worker(rank, world, port, mode, errq):
         from atomnas_b200.trainer import Trainer
         os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), LOCAL_RANK=str(rank),
                           WORLD_SIZE=str(world))
-        if mode == "graph_nccl":
-            os.environ["AN_GRAPH_NCCL"] = "1"
         udist.init_dist()
         g = torch.load(os.path.join(G, "tiny_supernet_train.pt"), weights_only=False)
 
@@ -90,14 +88,14 @@ def _worker(rank, world, port, mode, errq):
         raise
 
 
-@pytest.mark.parametrize("mode", ["eager", "graph_split"] + (["graph_nccl"] if os.environ.get("AN_TEST_GRAPH_NCCL") == "1" else []))
+@pytest.mark.parametrize("mode", ["eager", "graph_split"])
 def test_two_rank_nccl_step_parity(mode):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     errq = ctx.Queue()
-    port = 29500 + (os.getpid() % 1000) + {"eager": 0, "graph_split": 1, "graph_nccl": 2}[mode]
+    port = 29500 + (os.getpid() % 1000) + {"eager": 0, "graph_split": 1}[mode]
     procs = [ctx.Process(target=_worker, args=(r, 2, port, mode, errq)) for r in range(2)]
     for p in procs:
         p.start()
