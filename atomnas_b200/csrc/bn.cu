@@ -22,7 +22,23 @@ __device__ __forceinline__ bool reduce_partials(const float* __restrict__ part, 
   const int c = blockIdx.x * 32 + lc;
   double a = 0.0, b = 0.0;
   if (c < C) {
-    for (int r = lr; r < rows; r += kFinLanes) {
+    // 4 rows (8 loads) in flight per lane: the loop is pure load latency otherwise.  The summation
+    // order per lane is still r, r+8, r+16, ... (fixed -> deterministic).
+    int r = lr;
+    for (; r + 3 * kFinLanes < rows; r += 4 * kFinLanes) {
+      float v0[4], v1[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        v0[k] = part[(static_cast<long long>(r + k * kFinLanes) * 2 + 0) * C + c];
+        v1[k] = part[(static_cast<long long>(r + k * kFinLanes) * 2 + 1) * C + c];
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        a += static_cast<double>(v0[k]);
+        b += static_cast<double>(v1[k]);
+      }
+    }
+    for (; r < rows; r += kFinLanes) {
       a += static_cast<double>(part[(static_cast<long long>(r) * 2 + 0) * C + c]);
       b += static_cast<double>(part[(static_cast<long long>(r) * 2 + 1) * C + c]);
     }
@@ -105,7 +121,23 @@ __device__ __forceinline__ bool reduce_partials_seg(const float* __restrict__ pa
   const int c = blockIdx.x * 32 + lc;
   double a = 0.0, b = 0.0;
   if (c < C) {
-    for (int r = lr; r < rows; r += kFinLanes) {
+    // 4 rows (8 loads) in flight per lane: the loop is pure load latency otherwise.  The summation
+    // order per lane is still r, r+8, r+16, ... (fixed -> deterministic).
+    int r = lr;
+    for (; r + 3 * kFinLanes < rows; r += 4 * kFinLanes) {
+      float v0[4], v1[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        v0[k] = part[(static_cast<long long>(r + k * kFinLanes) * 2 + 0) * C + c];
+        v1[k] = part[(static_cast<long long>(r + k * kFinLanes) * 2 + 1) * C + c];
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        a += static_cast<double>(v0[k]);
+        b += static_cast<double>(v1[k]);
+      }
+    }
+    for (; r < rows; r += kFinLanes) {
       a += static_cast<double>(part[(static_cast<long long>(r) * 2 + 0) * C + c]);
       b += static_cast<double>(part[(static_cast<long long>(r) * 2 + 1) * C + c]);
     }

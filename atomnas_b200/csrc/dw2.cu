@@ -814,8 +814,18 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, int rows, in
   const int i = blockIdx.x * 32 + ex;
   const int n = taps * C;
   double a = 0.0;
-  if (i < n)
-    for (int r = rl; r < rows; r += 8) a += static_cast<double>(part[(long long)r * n + i]);
+  if (i < n) {
+    int r = rl;
+    for (; r + 24 < rows; r += 32) {              // 4 independent loads in flight per lane
+      const float v0 = part[(long long)r * n + i], v1 = part[(long long)(r + 8) * n + i];
+      const float v2 = part[(long long)(r + 16) * n + i], v3 = part[(long long)(r + 24) * n + i];
+      a += static_cast<double>(v0);
+      a += static_cast<double>(v1);
+      a += static_cast<double>(v2);
+      a += static_cast<double>(v3);
+    }
+    for (; r < rows; r += 8) a += static_cast<double>(part[(long long)r * n + i]);
+  }
   red[rl][ex] = a;
   __syncthreads();
   if (rl == 0 && i < n) {

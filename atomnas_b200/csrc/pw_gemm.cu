@@ -860,6 +860,10 @@ extern "C" int an_pw_gemm(const an_pw_gemm_args* a, void* stream) {
     const int avail = 227 * 1024 - 1024 - kAuxBytes - kGroupBytes - want_stages * stage_bytes;
     int nb = d.staged ? avail / per_buf : 2;
     if (nb > kMaxStaging) nb = kMaxStaging;
+    if (nb < 2 && a->a_mode != 2) {           // two tiles in flight matter more than a third operand stage
+      const int avail2 = avail + (want_stages - 2) * stage_bytes;
+      if (avail2 / per_buf >= 2) nb = 2;
+    }
     if (nb < 1) nb = 1;
     if (getenv("AN_PW_NBUF") != nullptr) { const int e = atoi(getenv("AN_PW_NBUF")); if (e >= 1 && e < nb) nb = e; }
     d.nbuf = nb;
