@@ -78,7 +78,7 @@ int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_
 
 int make_tmap_bf16_nhwc(CUtensorMap* tm, const void* base, uint64_t C, uint64_t W, uint64_t H,
                         uint64_t B, uint64_t ld_elems, uint32_t box_c, uint32_t box_w, uint32_t box_h,
-                        uint32_t box_n, bool oob_nan) {
+                        uint32_t box_n, bool oob_nan, int swizzle_bytes) {
   EncodeTiledFn fn = encode_fn();
   AN_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled unavailable (no CUDA driver / no sm_100 GPU)");
   cuuint64_t dims[4] = {C, W, H, B};
@@ -86,7 +86,10 @@ int make_tmap_bf16_nhwc(CUtensorMap* tm, const void* base, uint64_t C, uint64_t 
   cuuint32_t box[4] = {box_c, box_w, box_h, box_n};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                      : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE),
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   oob_nan ? CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA : CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   AN_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(4d) failed (%d): C=%llu W=%llu H=%llu B=%llu ld=%llu box=%ux%ux%u",
              (int)r, (unsigned long long)C, (unsigned long long)W, (unsigned long long)H, (unsigned long long)B,

@@ -57,10 +57,12 @@ int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_
 // 4-D bf16 NHWC tensor [B, H, W, C] (row pitch ld_elems per pixel), un-swizzled boxes
 // {box_c, box_w, box_h, 1}; coordinates may be negative / out of range (zero fill = conv padding;
 // oob_nan: NaN fill, for operands that pass through max(., 0) on load -- max(NaN, 0) = 0 keeps the
-// padding zero after an affine transform without any masking).
+// padding zero after an affine transform without any masking).  swizzle_bytes 32 / 64: the 16-byte
+// chunks of a box pixel (box_c * 2 bytes == swizzle_bytes) are XOR-permuted with address bits 7.. so
+// that the same channel group of consecutive pixels lands in different banks (dw_mma.cu).
 int make_tmap_bf16_nhwc(CUtensorMap* tm, const void* base, uint64_t C, uint64_t W, uint64_t H,
                         uint64_t B, uint64_t ld_elems, uint32_t box_c, uint32_t box_w, uint32_t box_h, uint32_t box_n = 1,
-                        bool oob_nan = false);
+                        bool oob_nan = false, int swizzle_bytes = 0);
 
 #ifdef __CUDACC__
 // ----------------------------------------------------------------------------------------------

@@ -55,9 +55,15 @@ DW_CASES = [
     (65, 7, 7, 384, 128, 256, 7, 1), (2, 56, 56, 32, 0, 32, 3, 1), (4, 20, 20, 16, 0, 16, 3, 1),
     (2, 7, 7, 40, 8, 24, 5, 1), (70, 16, 16, 72, 0, 72, 5, 2),
 ]
+# stride 1, k = 5 / 7, batch >= 8: the tensor-core path (dw_mma.cu) -- batch / width / channel remainders,
+# both column-tile configurations (W <= 8: one tile x 32 channels, else two tiles x 16 channels)
+MMA_CASES = [
+    (16, 14, 14, 208, 48, 96, 5, 1), (20, 28, 28, 144, 0, 144, 7, 1), (17, 56, 56, 24, 0, 24, 5, 1),
+    (33, 9, 9, 40, 8, 32, 7, 1), (16, 12, 20, 48, 0, 48, 7, 1), (8, 7, 7, 96, 0, 96, 5, 1), (40, 5, 5, 16, 0, 16, 7, 1),
+]
 
 
-@pytest.mark.parametrize("B,H,W,Ct,co,C,k,s", DW_CASES + [(3, 56, 56, 144, 0, 144, 7, 1), (3, 14, 14, 480, 0, 480, 5, 1), (2, 56, 56, 144, 0, 144, 5, 2)])
+@pytest.mark.parametrize("B,H,W,Ct,co,C,k,s", DW_CASES + MMA_CASES + [(3, 56, 56, 144, 0, 144, 7, 1), (3, 14, 14, 480, 0, 480, 5, 1), (2, 56, 56, 144, 0, 144, 5, 2)])
 @pytest.mark.parametrize("act", [0, 1, 2, 3])
 def test_dw_forward(B, H, W, Ct, co, C, k, s, act):
     torch.manual_seed(B * H + C + k)
@@ -82,7 +88,7 @@ def test_dw_forward(B, H, W, Ct, co, C, k, s, act):
     torch.testing.assert_close(st[1], (got * got).sum((0, 1, 2)), rtol=1e-3, atol=0.05)
 
 
-@pytest.mark.parametrize("B,H,W,Ct,co,C,k,s", DW_CASES + [(3, 56, 56, 144, 0, 144, 7, 1), (2, 56, 56, 144, 0, 144, 5, 2)])
+@pytest.mark.parametrize("B,H,W,Ct,co,C,k,s", DW_CASES + MMA_CASES + [(3, 56, 56, 144, 0, 144, 7, 1), (2, 56, 56, 144, 0, 144, 5, 2)])
 @pytest.mark.parametrize("act", [1, 2, 3])
 def test_dw_backward(B, H, W, Ct, co, C, k, s, act):
     if s == 2 and (H % 2 or W % 2):
