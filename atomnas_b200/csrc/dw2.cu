@@ -39,7 +39,8 @@ namespace an {
 int dw_stream_dgrad2_rows(int B, int C, int H, int W, int k);
 int dw_stream_dgrad2(const an_dw_bwd_args* a, cudaStream_t st);
 namespace dwm {                        // tensor-core path for stride 1 (dw_mma.cu)
-bool use(int k, int stride, int B);
+bool use_conv(int k, int stride, int B, int W);
+bool use_wgrad(int k, int stride, int B, int W);
 int fwd_rows(int B, int C, int H, int W, int k);
 int dgrad_rows(int B, int C, int H, int W, int k);
 int wgrad_rows(int B, int C, int H, int W, int k);
@@ -861,7 +862,7 @@ static inline void out_hw(int H, int W, int k, int s, int* Ho, int* Wo) {
 }
 
 extern "C" int an_dw_fwd_stats_rows(int B, int C, int Ho, int Wo, int k, int stride, int /*fused*/) {
-  if (dwm::use(k, stride, B)) return dwm::fwd_rows(B, C, Ho, Wo, k);
+  if (dwm::use_conv(k, stride, B, Wo)) return dwm::fwd_rows(B, C, Ho, Wo, k);
   return dw2::make_cfg(0, B, C, Ho, Wo, Ho * stride, k, stride).parts;
 }
 
@@ -870,13 +871,13 @@ extern "C" int an_dw_fwd(const an_dw_fwd_args* a, void* stream) {
   AN_REQUIRE(a->stride == 1 || a->stride == 2, "an_dw_fwd: stride %d unsupported", a->stride);
   AN_REQUIRE(a->C % 8 == 0 && a->ldx % 8 == 0 && a->ldy % 8 == 0, "an_dw_fwd: channels/pitches must be multiples of 8");
   AN_REQUIRE(a->scale == nullptr || a->shift != nullptr, "an_dw_fwd: scale without shift");
-  if (dwm::use(a->k, a->stride, a->B)) return dwm::fwd(a, static_cast<cudaStream_t>(stream));
+  if (dwm::use_conv(a->k, a->stride, a->B, a->W)) return dwm::fwd(a, static_cast<cudaStream_t>(stream));
   return dw2::fwd(a, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int an_dw_bwd_data_stats_rows(int B, int C, int H, int W, int k, int stride, int /*fused*/) {
   if (stride == 2) return dw_stream_dgrad2_rows(B, C, H, W, k);
-  if (dwm::use(k, stride, B)) return dwm::dgrad_rows(B, C, H, W, k);
+  if (dwm::use_conv(k, stride, B, W)) return dwm::dgrad_rows(B, C, H, W, k);
   return dw2::make_cfg(3, B, C, H, W, H, k, 1).parts;
 }
 
@@ -888,14 +889,14 @@ extern "C" int an_dw_bwd_data(const an_dw_bwd_args* a, void* stream) {
   AN_REQUIRE(a->ca == nullptr, "an_dw_bwd_data: pass the BN-backward-applied gradient dd in `g` (an_affine_act); "
                                "the on-load dd transform was removed with the tile kernels");
   if (a->stride == 2) return dw_stream_dgrad2(a, static_cast<cudaStream_t>(stream));
-  if (dwm::use(a->k, a->stride, a->B)) return dwm::bwd_data(a, static_cast<cudaStream_t>(stream));
+  if (dwm::use_conv(a->k, a->stride, a->B, a->W)) return dwm::bwd_data(a, static_cast<cudaStream_t>(stream));
   return dw2::bwd_data1(a, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int an_dw_bwd_weight_rows(int B, int C, int H, int W, int k, int stride, int /*fused*/) {
   int Ho, Wo;
   out_hw(H, W, k, stride, &Ho, &Wo);
-  if (dwm::use(k, stride, B)) return dwm::wgrad_rows(B, C, H, W, k);
+  if (dwm::use_wgrad(k, stride, B, W)) return dwm::wgrad_rows(B, C, H, W, k);
   return dw2::make_cfg(1, B, C, Ho, Wo, H, k, stride).parts;
 }
 
@@ -905,7 +906,7 @@ extern "C" int an_dw_bwd_weight(const an_dw_bwd_args* a, float* partials, float*
   AN_REQUIRE(a->C % 8 == 0 && partials && dw, "an_dw_bwd_weight: bad arguments");
   AN_REQUIRE(a->ca == nullptr, "an_dw_bwd_weight: pass the BN-backward-applied gradient dd in `g` (an_affine_act)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (int rc = dwm::use(a->k, a->stride, a->B) ? dwm::wgrad(a, partials, st) : dw2::wgrad(a, partials, st)) return rc;
+  if (int rc = dwm::use_wgrad(a->k, a->stride, a->B, a->W) ? dwm::wgrad(a, partials, st) : dw2::wgrad(a, partials, st)) return rc;
   const int taps = a->k * a->k;
   dw2::wgrad_reduce_kernel<<<(taps * a->C + 31) / 32, 256, 0, st>>>(
       partials, an_dw_bwd_weight_rows(a->B, a->C, a->H, a->W, a->k, a->stride, 0), taps, a->C, dw);

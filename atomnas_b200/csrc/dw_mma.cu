@@ -153,6 +153,14 @@ __device__ __forceinline__ void mma16816_z(float (&c)[4], const uint32_t (&a)[4]
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(0.f));
 }
 
+// mbarrier wait without the diagnostic printf of common.cuh (it is inlined 2 x K times here): a protocol bug
+// still traps instead of hanging the GPU.
+__device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity))
+    if (++spins > (1u << 26)) __trap();
+}
+
 // Shared-memory prologue of both kernels: zero the whole dynamic region (fragment loads read up to
 // one pixel past a tile -- multiplied by zero Toeplitz rows, but they must be finite), barriers.
 __device__ __forceinline__ void prologue(uint8_t* dsm, int bytes, uint64_t* full, uint64_t* empty, int D,
@@ -170,33 +178,6 @@ __device__ __forceinline__ void prologue(uint8_t* dsm, int bytes, uint64_t* full
     if (t1 != nullptr) tma_prefetch_desc(t1);
   }
   __syncthreads();
-}
-
-// One step of the forward / data-gradient ring for u = r mod K (static): the k MMAs per channel of
-// input row r (the first contribution to the newest output row starts from zero), then hand the row
-// finished by this step to the epilogue.
-template <int K, int U>
-__device__ __forceinline__ void conv_step(float (&acc)[K][4][4], float (&d)[4][4], const uint32_t (&a)[4][4],
-                                          const uint32_t (&bf)[4][K][2], const bool mma) {
-  constexpr int P = (K - 1) / 2;
-  if (mma) {
-#pragma unroll
-    for (int kh = 0; kh < K; ++kh) {
-      constexpr int dummy = 0;
-      (void)dummy;
-      const int slot = cmod(U + P - kh, K);                // output row r + P - kh
-#pragma unroll
-      for (int c4 = 0; c4 < 4; ++c4) {
-        if (kh == 0) mma16816_z(acc[slot][c4], a[c4], bf[c4][kh][0], bf[c4][kh][1]);
-        else mma16816(acc[slot][c4], a[c4], bf[c4][kh][0], bf[c4][kh][1]);
-      }
-    }
-  }
-  constexpr int sd = cmod(U - P, K);                         // output row r - P
-#pragma unroll
-  for (int c4 = 0; c4 < 4; ++c4)
-#pragma unroll
-    for (int i = 0; i < 4; ++i) d[c4][i] = acc[sd][c4][i];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -308,91 +289,105 @@ __global__ void __launch_bounds__(kThreads, 1) dwm_conv(const __grid_constant__ 
       for (int i = 0; i < 4; ++i) acc[s][c4][i] = 0.f;
   float2 st1a = make_float2(0.f, 0.f), st1b = st1a, st2a = st1a, st2b = st1a;
 
-  int u = 0, st = 0;                                         // r mod K, r mod D
-  uint32_t ph = 0;                                           // (r / D) & 1
-#pragma unroll 1
-  for (int r = 0; r < nsteps; ++r) {
-    if (producer) {
-      const int sn = r + D - 1;
-      if (sn < nsteps) {
-        const int pst = (st == 0) ? D - 1 : st - 1;          // the stage step r - 1 used = where step sn goes
-        if (r >= 1) mbar_wait(&empty[pst], (st == 0) ? (ph ^ 1u) : ph);
-        issue(sn, pst);
-      }
-    }
-    __syncwarp();
-    mbar_wait(&full[st], ph);
-    const uint8_t* sp = dsm + (size_t)st * p.stage_bytes;
-    uint32_t a[4][4];
-    const bool mma = r < p.H && !(p.exp & 4);
-    if (mma) {
-      uint32_t x[4][3];                                      // [channel][column group]: window columns 2t, 2t+1 (+8g)
+  // write-back of a staged row: 8 images x 16 columns x 64 bytes = 512 16-byte chunks, 2 per thread
+  // (chunk id = tid, tid + 256: image id >> 6, column (id & 63) >> 2, channel octet id & 3)
+  __nv_bfloat16* wb_dst[2];
+  uint32_t wb_src[2];
+  bool wb_ok[2];
 #pragma unroll
-      for (int cg = 0; cg < 3; ++cg) {
-        uint2 e = lds64(sp + oE + cg * (8 * kPix)), o = lds64(sp + oO + cg * (8 * kPix));
-        if (XF != 0) {
-          e.x = xform<XF>(e.x, xs01, xh01, hi6, xclamp); e.y = xform<XF>(e.y, xs23, xh23, hi6, xclamp);
-          o.x = xform<XF>(o.x, xs01, xh01, hi6, xclamp); o.y = xform<XF>(o.y, xs23, xh23, hi6, xclamp);
-          if (XF == 2 && imasked) {
-            if (!((imask >> (cg * 2)) & 1u)) e = make_uint2(0u, 0u);
-            if (!((imask >> (cg * 2 + 1)) & 1u)) o = make_uint2(0u, 0u);
+  for (int j = 0; j < 2; ++j) {
+    const int id = threadIdx.x + j * kThreads;
+    const int img = id >> 6, within = id & 63, col = within >> 2, part = within & 3;
+    wb_ok[j] = n0 + img < p.B && x0 + col < p.W && c0 + part * 8 < p.C;
+    wb_dst[j] = p.out + ((long long)(n0 + img) * p.H * p.W + x0 + col) * p.ldo + c0 + part * 8;
+    wb_src[j] = static_cast<uint32_t>(img * kOImg + within * 16);
+  }
+  const long long wb_row = (long long)p.W * p.ldo;
+
+  int st = 0;                                                // r mod D
+  uint32_t ph = 0;                                           // (r / D) & 1
+  // The ring period K is unrolled so that every accumulator slot is a compile-time register.
+#pragma unroll 1
+  for (int cb = 0; cb < nsteps; cb += K) {
+#pragma unroll
+    for (int u = 0; u < K; ++u) {
+      const int r = cb + u;
+      if (r < nsteps) {
+        if (producer) {
+          const int sn = r + D - 1;
+          if (sn < nsteps) {
+            const int pst = (st == 0) ? D - 1 : st - 1;      // the stage step r - 1 used = where step sn goes
+            if (r >= 1) wait_bar(&empty[pst], (st == 0) ? (ph ^ 1u) : ph);
+            issue(sn, pst);
           }
         }
-        x[0][cg] = __byte_perm(e.x, o.x, 0x5410); x[1][cg] = __byte_perm(e.x, o.x, 0x7632);
-        x[2][cg] = __byte_perm(e.y, o.y, 0x5410); x[3][cg] = __byte_perm(e.y, o.y, 0x7632);
-      }
-      // rows 0-7 = tile A (window columns 0..15), rows 8-15 = tile B (window columns 8..23)
+        __syncwarp();
+        wait_bar(&full[st], ph);
+        const uint8_t* sp = dsm + (size_t)st * p.stage_bytes;
+        if (r < p.H && !(p.exp & 4)) {
+          uint32_t a[4][4];
+          uint32_t x[4][3];                                  // [channel][column group]: window columns 2t, 2t+1 (+8 cg)
 #pragma unroll
-      for (int c4 = 0; c4 < 4; ++c4) { a[c4][0] = x[c4][0]; a[c4][1] = x[c4][1]; a[c4][2] = x[c4][1]; a[c4][3] = x[c4][2]; }
-    }
-    float d[4][4];
-    const bool do_mma = mma && !(p.exp & 2);
-    switch (u) {
-      case 0: conv_step<K, 0>(acc, d, a, bf, do_mma); break;
-      case 1: conv_step<K, 1>(acc, d, a, bf, do_mma); break;
-      case 2: conv_step<K, 2>(acc, d, a, bf, do_mma); break;
-      case 3: if (K > 3) conv_step<K, (K > 3 ? 3 : 0)>(acc, d, a, bf, do_mma); break;
-      case 4: if (K > 3) conv_step<K, (K > 3 ? 4 : 0)>(acc, d, a, bf, do_mma); break;
-      case 5: if (K > 5) conv_step<K, (K > 5 ? 5 : 0)>(acc, d, a, bf, do_mma); break;
-      default: if (K > 5) conv_step<K, (K > 5 ? 6 : 0)>(acc, d, a, bf, do_mma); break;
-    }
-    const int od = r - P;                                    // the output row finished by this step
-    if (od >= 0 && !(p.exp & 1)) {
-      uint8_t* ob = ost + (od & 1) * kOst;
+          for (int cg = 0; cg < 3; ++cg) {
+            uint2 e = lds64(sp + oE + cg * (8 * kPix)), o = lds64(sp + oO + cg * (8 * kPix));
+            if (XF != 0) {
+              e.x = xform<XF>(e.x, xs01, xh01, hi6, xclamp); e.y = xform<XF>(e.y, xs23, xh23, hi6, xclamp);
+              o.x = xform<XF>(o.x, xs01, xh01, hi6, xclamp); o.y = xform<XF>(o.y, xs23, xh23, hi6, xclamp);
+              if (XF == 2 && imasked) {
+                if (!((imask >> (cg * 2)) & 1u)) e = make_uint2(0u, 0u);
+                if (!((imask >> (cg * 2 + 1)) & 1u)) o = make_uint2(0u, 0u);
+              }
+            }
+            x[0][cg] = __byte_perm(e.x, o.x, 0x5410); x[1][cg] = __byte_perm(e.x, o.x, 0x7632);
+            x[2][cg] = __byte_perm(e.y, o.y, 0x5410); x[3][cg] = __byte_perm(e.y, o.y, 0x7632);
+          }
+          // rows 0-7 = tile A (window columns 0..15), rows 8-15 = tile B (window columns 8..23)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {                          // i = odd column | tile << 1
-        float2 v01 = make_float2(d[0][i], d[1][i]), v23 = make_float2(d[2][i], d[3][i]);
-        float2 x01 = make_float2(0.f, 0.f), x23 = x01;
-        if (EBN) {
-          const uint2 e = lds64(sp + ((i & 1) ? oXo : oXe) + (i >> 1) * (8 * kPix));
-          x01 = unpack2(e.x); x23 = unpack2(e.y);
-          v01 = mul2(v01, act_grad2<SWISH>(fma2(es01, x01, eh01), elo, ehi));
-          v23 = mul2(v23, act_grad2<SWISH>(fma2(es23, x23, eh23), elo, ehi));
+          for (int c4 = 0; c4 < 4; ++c4) { a[c4][0] = x[c4][0]; a[c4][1] = x[c4][1]; a[c4][2] = x[c4][1]; a[c4][3] = x[c4][2]; }
+          if (!(p.exp & 2)) {
+#pragma unroll
+            for (int kh = 0; kh < K; ++kh) {
+              const int slot = cmod(u + P - kh, K);          // output row r + P - kh; kh = 0 opens it (C = 0)
+#pragma unroll
+              for (int c4 = 0; c4 < 4; ++c4) {
+                if (kh == 0) mma16816_z(acc[slot][c4], a[c4], bf[c4][kh][0], bf[c4][kh][1]);
+                else mma16816(acc[slot][c4], a[c4], bf[c4][kh][0], bf[c4][kh][1]);
+              }
+            }
+          }
         }
-        uint32_t lo = pack_bf16(v01.x, v01.y), hi = pack_bf16(v23.x, v23.y);
-        if (omasked && !((omask >> i) & 1u)) { lo = 0u; hi = 0u; }
-        const float2 f01 = unpack2(lo), f23 = unpack2(hi);
-        st1a = add2(st1a, f01); st1b = add2(st1b, f23);
-        st2a = fma2(f01, EBN ? fma2(x01, er01, em01) : f01, st2a);
-        st2b = fma2(f23, EBN ? fma2(x23, er23, em23) : f23, st2b);
-        *reinterpret_cast<uint2*>(ob + oS + (i & 1) * kPix + (i >> 1) * (8 * kPix)) = make_uint2(lo, hi);
-      }
-      __syncthreads();
-      // coalesced write-back of the staged row: 8 images x 16 columns x 64 bytes = 512 chunks, 2 per thread
+        const int od = r - P;                                // the output row finished by this step
+        const int sd = cmod(u - P, K);
+        if (od >= 0 && !(p.exp & 1)) {
+          uint8_t* ob = ost + (od & 1) * kOst;
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int id = threadIdx.x + j * kThreads;
-        const int img = id >> 6, within = id & 63, col = within >> 2, part = within & 3;
-        if (n0 + img < p.B && x0 + col < p.W && c0 + part * 8 < p.C) {
-          const uint4 v = *reinterpret_cast<const uint4*>(ob + img * kOImg + within * 16);
-          *reinterpret_cast<uint4*>(p.out + (((long long)(n0 + img) * p.H + od) * p.W + x0 + col) * p.ldo + c0 + part * 8) = v;
+          for (int i = 0; i < 4; ++i) {                      // i = odd column | tile << 1
+            float2 v01 = make_float2(acc[sd][0][i], acc[sd][1][i]), v23 = make_float2(acc[sd][2][i], acc[sd][3][i]);
+            float2 x01 = make_float2(0.f, 0.f), x23 = x01;
+            if (EBN) {
+              const uint2 e = lds64(sp + ((i & 1) ? oXo : oXe) + (i >> 1) * (8 * kPix));
+              x01 = unpack2(e.x); x23 = unpack2(e.y);
+              v01 = mul2(v01, act_grad2<SWISH>(fma2(es01, x01, eh01), elo, ehi));
+              v23 = mul2(v23, act_grad2<SWISH>(fma2(es23, x23, eh23), elo, ehi));
+            }
+            uint32_t lo = pack_bf16(v01.x, v01.y), hi = pack_bf16(v23.x, v23.y);
+            if (omasked && !((omask >> i) & 1u)) { lo = 0u; hi = 0u; }
+            const float2 f01 = unpack2(lo), f23 = unpack2(hi);       // statistics of the STORED (rounded) tensor
+            st1a = add2(st1a, f01); st1b = add2(st1b, f23);
+            st2a = fma2(f01, EBN ? fma2(x01, er01, em01) : f01, st2a);
+            st2b = fma2(f23, EBN ? fma2(x23, er23, em23) : f23, st2b);
+            *reinterpret_cast<uint2*>(ob + oS + (i & 1) * kPix + (i >> 1) * (8 * kPix)) = make_uint2(lo, hi);
+          }
+          __syncthreads();
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            if (wb_ok[j]) *reinterpret_cast<uint4*>(wb_dst[j] + od * wb_row) = *reinterpret_cast<const uint4*>(ob + wb_src[j]);
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[st]);
+        if (++st == D) { st = 0; ph ^= 1u; }
       }
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[st]);
-    u = (u + 1 == K) ? 0 : u + 1;
-    if (++st == D) { st = 0; ph ^= 1u; }
   }
   if (p.stats_part != nullptr) {
     float sv[8] = {st1a.x, st1a.y, st1b.x, st1b.y, st2a.x, st2a.y, st2b.x, st2b.y};
@@ -419,21 +414,6 @@ __global__ void __launch_bounds__(kThreads, 1) dwm_conv(const __grid_constant__ 
 // pair (r, kh) meets dd row r + P - kh = s - kh.  MMA: m = window column (16), k = image (16),
 // n = output column (8).
 // ------------------------------------------------------------------------------------------------
-template <int K, int U>
-__device__ __forceinline__ void wgrad_step(float (&acc)[K][4][4], uint32_t (&bd)[K][4][2], const uint32_t (&a)[4][4],
-                                           const uint32_t (&nb)[4][2], const bool mma) {
-#pragma unroll
-  for (int c4 = 0; c4 < 4; ++c4) { bd[U][c4][0] = nb[c4][0]; bd[U][c4][1] = nb[c4][1]; }
-  if (mma) {
-#pragma unroll
-    for (int kh = 0; kh < K; ++kh) {
-      const int slot = cmod(U - kh, K);                      // dd row s - kh
-#pragma unroll
-      for (int c4 = 0; c4 < 4; ++c4) mma16816(acc[kh][c4], a[c4], bd[slot][c4][0], bd[slot][c4][1]);
-    }
-  }
-}
-
 template <int K, int XF>
 __global__ void __launch_bounds__(kThreads, 1) dwm_wgrad(const __grid_constant__ Params p) {
   extern __shared__ uint8_t dsm_raw[];
@@ -498,63 +478,63 @@ __global__ void __launch_bounds__(kThreads, 1) dwm_wgrad(const __grid_constant__
       bd[s][c4][0] = 0u; bd[s][c4][1] = 0u;
     }
 
-  int u = 0, st = 0;
+  int st = 0;
   uint32_t ph = 0;
 #pragma unroll 1
-  for (int s = 0; s < nsteps; ++s) {
-    if (producer) {
-      const int sn = s + D - 1;
-      if (sn < nsteps) {
-        const int pst = (st == 0) ? D - 1 : st - 1;
-        if (s >= 1) mbar_wait(&empty[pst], (st == 0) ? (ph ^ 1u) : ph);
-        issue(sn, pst);
+  for (int cb = 0; cb < nsteps; cb += K) {
+#pragma unroll
+    for (int u = 0; u < K; ++u) {
+      const int s = cb + u;
+      if (s < nsteps) {
+        if (producer) {
+          const int sn = s + D - 1;
+          if (sn < nsteps) {
+            const int pst = (st == 0) ? D - 1 : st - 1;
+            if (s >= 1) wait_bar(&empty[pst], (st == 0) ? (ph ^ 1u) : ph);
+            issue(sn, pst);
+          }
+        }
+        __syncwarp();
+        wait_bar(&full[st], ph);
+        const uint8_t* sp = dsm + (size_t)st * p.stage_bytes;
+#pragma unroll
+        for (int i8 = 0; i8 < 2; ++i8) {                     // dd row s -> ring slot u
+          const uint2 e = lds64(sp + oBe + i8 * dBI), o = lds64(sp + oBo + i8 * dBI);
+          bd[u][0][i8] = __byte_perm(e.x, o.x, 0x5410); bd[u][1][i8] = __byte_perm(e.x, o.x, 0x7632);
+          bd[u][2][i8] = __byte_perm(e.y, o.y, 0x5410); bd[u][3][i8] = __byte_perm(e.y, o.y, 0x7632);
+        }
+        const int r = s - P;
+        if (r >= 0 && r < p.H) {
+          uint32_t a[4][4];
+#pragma unroll
+          for (int i8 = 0; i8 < 2; ++i8)
+#pragma unroll
+            for (int c8 = 0; c8 < 2; ++c8) {
+              uint2 e = lds64(sp + oE + i8 * dI + c8 * dC), o = lds64(sp + oO + i8 * dI + c8 * dC);
+              if (XF != 0) {
+                e.x = xform<XF>(e.x, xs01, xh01, hi6, xclamp); e.y = xform<XF>(e.y, xs23, xh23, hi6, xclamp);
+                o.x = xform<XF>(o.x, xs01, xh01, hi6, xclamp); o.y = xform<XF>(o.y, xs23, xh23, hi6, xclamp);
+                if (XF == 2 && imasked) {
+                  if (!((imask >> (i8 * 2 + c8 * 4)) & 1u)) e = make_uint2(0u, 0u);
+                  if (!((imask >> (i8 * 2 + c8 * 4 + 1)) & 1u)) o = make_uint2(0u, 0u);
+                }
+              }
+              const int ri = i8 * 2 + c8;                    // a0: (col g, imgs lo) a1: (col g+8, lo) a2: (g, hi) a3: (g+8, hi)
+              a[0][ri] = __byte_perm(e.x, o.x, 0x5410); a[1][ri] = __byte_perm(e.x, o.x, 0x7632);
+              a[2][ri] = __byte_perm(e.y, o.y, 0x5410); a[3][ri] = __byte_perm(e.y, o.y, 0x7632);
+            }
+#pragma unroll
+          for (int kh = 0; kh < K; ++kh) {
+            const int slot = cmod(u - kh, K);                // dd row s - kh
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) mma16816(acc[kh][c4], a[c4], bd[slot][c4][0], bd[slot][c4][1]);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[st]);
+        if (++st == D) { st = 0; ph ^= 1u; }
       }
     }
-    __syncwarp();
-    mbar_wait(&full[st], ph);
-    const uint8_t* sp = dsm + (size_t)st * p.stage_bytes;
-    uint32_t nb[4][2];                                       // dd row s
-#pragma unroll
-    for (int i8 = 0; i8 < 2; ++i8) {
-      const uint2 e = lds64(sp + oBe + i8 * dBI), o = lds64(sp + oBo + i8 * dBI);
-      nb[0][i8] = __byte_perm(e.x, o.x, 0x5410); nb[1][i8] = __byte_perm(e.x, o.x, 0x7632);
-      nb[2][i8] = __byte_perm(e.y, o.y, 0x5410); nb[3][i8] = __byte_perm(e.y, o.y, 0x7632);
-    }
-    const int r = s - P;
-    const bool mma = r >= 0 && r < p.H;
-    uint32_t a[4][4];
-    if (mma) {
-#pragma unroll
-      for (int i8 = 0; i8 < 2; ++i8)
-#pragma unroll
-        for (int c8 = 0; c8 < 2; ++c8) {
-          uint2 e = lds64(sp + oE + i8 * dI + c8 * dC), o = lds64(sp + oO + i8 * dI + c8 * dC);
-          if (XF != 0) {
-            e.x = xform<XF>(e.x, xs01, xh01, hi6, xclamp); e.y = xform<XF>(e.y, xs23, xh23, hi6, xclamp);
-            o.x = xform<XF>(o.x, xs01, xh01, hi6, xclamp); o.y = xform<XF>(o.y, xs23, xh23, hi6, xclamp);
-            if (XF == 2 && imasked) {
-              if (!((imask >> (i8 * 2 + c8 * 4)) & 1u)) e = make_uint2(0u, 0u);
-              if (!((imask >> (i8 * 2 + c8 * 4 + 1)) & 1u)) o = make_uint2(0u, 0u);
-            }
-          }
-          const int ri = i8 * 2 + c8;                        // a0: (col g, imgs lo) a1: (col g+8, lo) a2: (g, hi) a3: (g+8, hi)
-          a[0][ri] = __byte_perm(e.x, o.x, 0x5410); a[1][ri] = __byte_perm(e.x, o.x, 0x7632);
-          a[2][ri] = __byte_perm(e.y, o.y, 0x5410); a[3][ri] = __byte_perm(e.y, o.y, 0x7632);
-        }
-    }
-    switch (u) {
-      case 0: wgrad_step<K, 0>(acc, bd, a, nb, mma); break;
-      case 1: wgrad_step<K, 1>(acc, bd, a, nb, mma); break;
-      case 2: wgrad_step<K, 2>(acc, bd, a, nb, mma); break;
-      case 3: if (K > 3) wgrad_step<K, (K > 3 ? 3 : 0)>(acc, bd, a, nb, mma); break;
-      case 4: if (K > 3) wgrad_step<K, (K > 3 ? 4 : 0)>(acc, bd, a, nb, mma); break;
-      case 5: if (K > 5) wgrad_step<K, (K > 5 ? 5 : 0)>(acc, bd, a, nb, mma); break;
-      default: if (K > 5) wgrad_step<K, (K > 5 ? 6 : 0)>(acc, bd, a, nb, mma); break;
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[st]);
-    u = (u + 1 == K) ? 0 : u + 1;
-    if (++st == D) { st = 0; ph ^= 1u; }
   }
   // every warp is done with the ring: reuse it for the 16 x 8 correlation blocks, then sum diagonals
   __syncthreads();
@@ -683,17 +663,29 @@ static Kernel wgrad_kernel(int xf) {
   }
 }
 
-// Which (k, stride, batch) shapes run here: stride 1, at least one image tile, k in AN_DW_MMA
-// (digits; default "57", "0" = never -- the A/B switch of scripts/bench_kernels.py).
-bool use(int k, int stride, int B) {
-  static const char* sel = [] {
-    const char* e = getenv("AN_DW_MMA");
-    return e != nullptr ? e : "57";
-  }();
-  if (stride != 1 || B < 8) return false;
-  for (const char* c = sel; *c; ++c)
+// Which shapes run here (stride 1, at least one 8-image tile).  Measured on B200 at batch 256
+// (profiles/r02_dw_mma_sweep.json): the banded MMA beats the FFMA2 row-streaming kernels for k = 7 at
+// widths >= 14 (forward / data gradient 1.1-1.4x, weight gradient 1.3-2.0x) and for the k = 5 weight
+// gradient except at width 28; k = 3 and the 7 x 7 maps stay on dw2.cu.  AN_DW_MMA = digits forces those
+// kernel sizes onto this path for every width ("0" = never) -- the A/B switch of scripts/bench_kernels.py.
+static const char* forced() {
+  static const char* sel = getenv("AN_DW_MMA");
+  return sel;
+}
+static bool forced_has(int k) {
+  for (const char* c = forced(); *c; ++c)
     if (*c - '0' == k) return true;
   return false;
+}
+bool use_conv(int k, int stride, int B, int W) {
+  if (stride != 1 || B < 8) return false;
+  if (forced() != nullptr) return forced_has(k);
+  return k == 7 && W >= 14;
+}
+bool use_wgrad(int k, int stride, int B, int W) {
+  if (stride != 1 || B < 8) return false;
+  if (forced() != nullptr) return forced_has(k);
+  return (k == 7 && W >= 7) || (k == 5 && W >= 14 && W != 28);
 }
 
 int fwd_rows(int B, int C, int H, int W, int k) { return make_cfg(0, B, C, H, W, k).parts; }

@@ -309,12 +309,13 @@ def _qb(x): return _Round.apply(x, False, True)      # only the gradient is stor
 def _qw(w): return w + (w.to(torch.bfloat16).to(w.dtype) - w).detach()   # bf16 weight copy
 
 
-def dw_on_tensor_cores(k, stride, batch):
-    """Which depthwise layers the engine runs as banded tensor-core products (csrc/dw_mma.cu: stride 1,
-    k = 5 / 7, at least 8 images): there BOTH operands are bf16 -- the activated input is rounded after
-    the on-load BN + activation and the taps are the bf16 rounding of the fp32 master (exactly what an
-    autocast convolution multiplies).  The other layers keep fp32 taps and an unrounded operand."""
-    return stride == 1 and k in (5, 7) and batch >= 8
+def dw_on_tensor_cores(k, stride, batch, width):
+    """Which depthwise layers the engine's FORWARD runs as banded tensor-core products (csrc/dw_mma.cu
+    use_conv: stride 1, k = 7, at least 8 images, maps at least 14 wide): there BOTH operands are bf16 --
+    the activated input is rounded after the on-load BN + activation and the taps are the bf16
+    rounding of the fp32 master (exactly what an autocast convolution multiplies).  The other layers
+    keep fp32 taps and an unrounded operand."""
+    return stride == 1 and k == 7 and batch >= 8 and width >= 14
 
 
 def block_forward_bf16_points(spec, st, b, y, training=True):
@@ -333,11 +334,11 @@ def block_forward_bf16_points(spec, st, b, y, training=True):
             # expand output ON LOAD, in fp32 -- the activated operand is not rounded.  Swish: the engine
             # materialises act(bn(.)) as a bf16 tensor first (exp on the load path is too dear).
             t = act(_qb(_bn(spec, st, base + ".0.1", t, training)), a)
-            if a == "nn.Swish" or dw_on_tensor_cores(k, b.stride, y.shape[0]):
+            if a == "nn.Swish" or dw_on_tensor_cores(k, b.stride, y.shape[0], y.shape[3]):
                 t = _qf(t)
             d = 1
         wd = st["%s.%d.0.weight" % (base, d)]
-        if dw_on_tensor_cores(k, b.stride, y.shape[0]):
+        if dw_on_tensor_cores(k, b.stride, y.shape[0], y.shape[3]):
             wd = _qw(wd)
         t = _q2(F.conv2d(t, wd, None, b.stride, (k - 1) // 2, 1, h))
         t = _qf(act(_qb(_bn(spec, st, "%s.%d.1" % (base, d), t, training)), a))

@@ -143,6 +143,17 @@ def test_dw_backward(B, H, W, Ct, co, C, k, s, act):
     assert (dw - wref).abs().max().item() <= 2e-3 * wref.abs().max().item() + 1e-3
 
 
+def test_dw_tensor_core_path_forced():
+    """The per-shape dispatch (dw_mma.cu use_conv / use_wgrad) sends only the shapes where the banded MMA
+    wins to the tensor cores; AN_DW_MMA=357 forces every stride-1 case of this file with >= 8 images
+    through it (the switch is read once per process, hence the subprocess)."""
+    import subprocess
+    env = dict(os.environ, AN_DW_MMA="357")
+    res = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider",
+                          "-k", "test_dw_forward or test_dw_backward"], env=env, capture_output=True, text=True, cwd=ROOT)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
+
+
 def test_bn_finalize_and_backward_coefficients():
     torch.manual_seed(0)
     M, C = 5000, 72
