@@ -129,8 +129,12 @@ struct Dgrad2Geom {
   static constexpr int U = (K + 1) / 2;                      // dd rows per stage == unroll period
 };
 
+// k = 3 fits 128 registers: two CTAs per SM (4 warps per scheduler) hide the shared-memory and
+// store latencies the k = 5 / 7 builds (1 CTA; k = 5 spills at 128 registers) have to eat.
+__host__ __device__ constexpr int dgrad2_blocks(int K) { return K == 3 ? 2 : 1; }
+
 template <int K, int TC, bool SWISH>
-__global__ void __launch_bounds__(kMaxThreads, 1) dw_dgrad2_stream(const __grid_constant__ DwStreamParams p) {
+__global__ void __launch_bounds__(kMaxThreads, dgrad2_blocks(K)) dw_dgrad2_stream(const __grid_constant__ DwStreamParams p) {
   extern __shared__ __align__(128) uint8_t dsm[];
   using G = Dgrad2Geom<K, TC>;
   constexpr int P = G::P, TLO = G::TLO, NX = G::NX, RB = G::RB, U = G::U;
@@ -319,13 +323,15 @@ static StreamCfg dgrad2_cfg(int B, int C, int Ht, int Wt, int k) {
   const int rows = (Ht - 1 + P) / 2 - TLO + 1;                 // dd rows TLO .. floor((H-1+P)/2)
   const size_t stage = (size_t)U * c.PW * 128 + (size_t)(k + 1) * TW * 128;
   c.nch = (rows + U - 1) / U;
-  int depth = static_cast<int>((96 * 1024) / stage);
+  const int minb = dgrad2_blocks(k);
+  int depth = static_cast<int>(((200 * 1024) / minb - 4096) / stage);
   if (depth > 6) depth = 6;
+  if (depth > c.nch + 1) depth = c.nch + 1;
   if (depth < 2) depth = 2;
   c.depth = depth;
   c.smem = (size_t)depth * stage + 2 * depth * 8 + (size_t)c.nwc * 2 * 64 * 4 + 128;
   long long ctas1 = (long long)c.strips * cblocks * c.groups;
-  int ipb = static_cast<int>(ctas1 / (4LL * sm_count()));
+  int ipb = static_cast<int>(ctas1 / (4LL * sm_count() * minb));
   if (ipb < 1) ipb = 1;
   if (ipb > 16) ipb = 16;
   c.ipb = ipb;
