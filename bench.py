@@ -184,8 +184,10 @@ def timed_loop(fn, steps, world):
 CLASSES = {"an_dw_fwd": "depthwise", "an_dw_bwd_data": "depthwise", "an_dw_bwd_weight": "depthwise",
            "an_dw_bwd": "depthwise",
            "an_pw_gemm": "pointwise", "an_pw_wgrad": "pointwise", "an_wgrad_reduce": "pointwise",
+           "an_wgrad_reduce_multi": "pointwise",
            "an_affine_act": "elementwise", "an_col_reduce": "elementwise", "an_act_bwd_reduce": "elementwise",
-           "an_bn_finalize": "bn_finalize", "an_bn_bwd_finalize": "bn_finalize"}
+           "an_bn_finalize": "bn_finalize", "an_bn_bwd_finalize": "bn_finalize",
+           "an_bn_finalize_multi": "bn_finalize", "an_bn_bwd_finalize_multi": "bn_finalize"}
 
 
 def algorithmic_work(eng, B):

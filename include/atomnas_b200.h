@@ -105,7 +105,8 @@ int an_wgrad_reduce_multi(const float* partials, int splits, int Cbig, int Csmal
                           const an_wg_seg* segs, int nseg, void* stream);
 
 /* ------------------------------------------------------------------------------------------
- * Depthwise k x k convolution (k = 3, 5, 7; stride 1, 2; pad (k-1)/2), NHWC bf16, CUDA cores.
+ * Depthwise k x k convolution (k = 3, 5, 7; stride 1, 2; pad (k-1)/2), NHWC bf16: CUDA cores
+ * (FFMA2 row streaming) or, for the shapes where it measured faster, the warp-level tensor cores.
  * Replaces ConvBNReLU(h, h, k, stride, groups=h) models/mobilenet_base.py:330-336 (pad :133)
  * and its autograd backward.  Pointers are pre-offset to the branch's first channel; C is the
  * branch width, ld* the full row pitch of the (branch-fused) tensor.
@@ -118,7 +119,12 @@ int an_wgrad_reduce_multi(const float* partials, int splits, int Cbig, int Csmal
  * The producer's BatchNorm + activation is applied ON LOAD by the forward and weight-gradient
  * kernels (scale / e_scale != NULL), so the activated operand is never materialised in HBM.
  * Row-streaming kernels: csrc/dw2.cu (forward, stride-1 data gradient, weight gradient) and
- * csrc/dw_stream.cu (stride-2 data gradient).  ca / cb / cc must be NULL (the on-load BN-backward
+ * csrc/dw_stream.cu (stride-2 data gradient).  Tensor-core kernels: csrc/dw_mma.cu -- stride 1, at
+ * least 8 images, k = 7 forward / data gradient on maps >= 14 wide, k = 7 weight gradient, k = 5 weight
+ * gradient on maps 14 / 56 wide; there the activated operand and the taps are multiplied in bf16
+ * (fp32 accumulation), everywhere else in fp32.  AN_DW_MMA=<digits> forces those kernel sizes onto
+ * the tensor cores for every width ("0": never); the *_rows helpers follow the same rule.
+ * ca / cb / cc must be NULL (the on-load BN-backward
  * transform of g was removed together with the tile kernels); draw is unused.  The `fused`
  * argument of the *_rows helpers is ignored (one kernel family serves both operand forms).
  * ------------------------------------------------------------------------------------------ */

@@ -12,7 +12,7 @@ import json
 import re
 import sys
 
-CLASS_OF = [("dw2_conv", "depthwise"), ("dw2_wgrad", "depthwise"), ("dw_dgrad2", "depthwise"), ("dw2::wgrad_reduce", "depthwise"),
+CLASS_OF = [("dwm_conv", "depthwise"), ("dwm_wgrad", "depthwise"), ("dw2_conv", "depthwise"), ("dw2_wgrad", "depthwise"), ("dw_dgrad2", "depthwise"), ("dw2::wgrad_reduce", "depthwise"),
             ("pw_gemm", "pointwise"), ("pw_wgrad", "pointwise"), ("wgrad_reduce", "pointwise"),
             ("affine_act", "elementwise"), ("col_reduce", "elementwise"), ("act_bwd_reduce", "elementwise"),
             ("bn_finalize", "bn_finalize"), ("bn_bwd_finalize", "bn_finalize")]

@@ -14,7 +14,7 @@ def last_line(name):
 
 
 def test_committed_bench_line_has_every_contract_key():
-    d = last_line("r01e_bench_n1.json")
+    d = last_line("r02_bench_n1.json")
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
               "scaling", "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches",
               "roofline", "cpu_baseline"):
@@ -31,15 +31,36 @@ def test_committed_bench_line_has_every_contract_key():
     assert r["bound"] in ("hbm", "tensor") and r["unit"] in ("GB/s", "TFLOP/s")
     assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-3 and "traffic" in r
     c = d["cpu_baseline"]
-    assert c["kind"] in ("port", "reference") and c["cores"] >= 1 and c["value"] > 0 and c["sample"]
+    assert c["kind"] == "reference" and c["cores"] >= 1 and c["value"] > 0 and "unmodified reference" in c["sample"]
+    assert r["kernel"] == "depthwise" and r["algorithmic_bytes_per_step"] > 0
+    classes = {k["class"]: k for k in d["kernel_classes"]}
+    assert {"depthwise", "pointwise", "elementwise", "bn_finalize"} <= set(classes)
+    assert abs(sum(k["ms_per_step"] for k in d["kernel_classes"]) - d["ms_per_step"]) / d["ms_per_step"] < 0.15
     assert d["clocks"]["reasons"] == [] and d["clocks"]["sm_mhz"] > 0.8 * d["clocks"]["sm_max_mhz"]
 
 
 def test_committed_reference_arm_line():
-    d = last_line("r01b_bench_ref.json")
+    d = last_line("r02_bench_reference.json")
     assert d["impl"] == "reference" and d["unit"] == "images/sec" and d["value"] > 0
     assert d["e2e"] == {"value": d["value"], "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["value"] == d["value"]
+    assert d["config"]["workload"] == last_line("r02_bench_n1.json")["config"]["workload"]
+
+
+def test_committed_series_lines():
+    """AtomNAS-A, the shrink series (mask fixtures), the (S) fixed-global-batch series and the cuDNN bar."""
+    base = last_line("r02_bench_n1.json")
+    a = last_line("r02_bench_atomnas_a.json")
+    assert a["config"]["model"] == "atomnas_a" and a["value"] > 0 and a["gpu_launches"] > 0
+    rnd, srch = last_line("r02_bench_masks_random.json"), last_line("r02_bench_masks_searched.json")
+    assert rnd["config"]["masks"] == "random" and srch["config"]["masks"] == "searched"
+    assert srch["value"] > rnd["value"] > base["value"]          # shrinking speeds the step up
+    acc = last_line("r02_bench_accum8.json")
+    assert acc["config"]["accum"] == 8 and acc["config"]["global_batch"] == 8 * 256
+    assert abs(acc["value"] - base["value"]) / base["value"] < 0.05
+    for name, mode in (("r02_bench_refgpu_bf16.json", "bf16"), ("r02_bench_refgpu_fp32.json", "fp32")):
+        g = last_line(name)
+        assert g["impl"] == "reference-gpu" and g["value"] > 0 and base["value"] / g["value"] > 3.0
 
 
 def test_bench_defaults_and_workload():
