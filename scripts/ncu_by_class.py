@@ -40,6 +40,8 @@ def main():
     classes, kernels = {}, {}
     for e in per.values():
         cls = next((c for pat, c in CLASS_OF if pat in e["name"]), "other")
+        if "at::" in e["name"] or "at_cuda_detail" in e["name"]:
+            cls = "torch_setup"          # arena / optimizer-state / input initialisation of the process, not the step
         short = re.sub(r"\(.*", "", e["name"]).replace("void ", "").replace("an::", "")[:60]
         for table, key in ((classes, cls), (kernels, short)):
             t = table.setdefault(key, {"launches": 0, "time_ns": 0.0, "dram_read": 0.0, "dram_write": 0.0})
@@ -47,7 +49,7 @@ def main():
             t["time_ns"] += e.get("gpu__time_duration.sum", 0.0)
             t["dram_read"] += e.get("dram__bytes_read.sum", 0.0)
             t["dram_write"] += e.get("dram__bytes_write.sum", 0.0)
-    total = sum(t["time_ns"] for t in classes.values())
+    total = sum(t["time_ns"] for c, t in classes.items() if c != "torch_setup")
     out = {"model": model, "batch": batch, "steps_captured": steps,
            "how": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none "
                   "on scripts/profile_step.py (one eager step; per-launch times are cold-cache and serialised: compare shares)",
