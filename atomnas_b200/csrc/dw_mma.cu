@@ -138,7 +138,6 @@ struct Params {
   int depth, pwb, pwa;
   int in_bytes, stage_bytes, in_tx, aux_tx, smem_bytes;
   int ragged;
-  int exp;                            // AN_DWM_EXP bit mask: timing experiments only (results are wrong)
 };
 
 constexpr int kCC = 32;               // channels per CTA = 8 warps x 4
@@ -324,7 +323,7 @@ __global__ void __launch_bounds__(kThreads, 1) dwm_conv(const __grid_constant__ 
         __syncwarp();
         wait_bar(&full[st], ph);
         const uint8_t* sp = dsm + (size_t)st * p.stage_bytes;
-        if (r < p.H && !(p.exp & 4)) {
+        if (r < p.H) {
           uint32_t a[4][4];
           uint32_t x[4][3];                                  // [channel][column group]: window columns 2t, 2t+1 (+8 cg)
 #pragma unroll
@@ -344,21 +343,19 @@ __global__ void __launch_bounds__(kThreads, 1) dwm_conv(const __grid_constant__ 
           // rows 0-7 = tile A (window columns 0..15), rows 8-15 = tile B (window columns 8..23)
 #pragma unroll
           for (int c4 = 0; c4 < 4; ++c4) { a[c4][0] = x[c4][0]; a[c4][1] = x[c4][1]; a[c4][2] = x[c4][1]; a[c4][3] = x[c4][2]; }
-          if (!(p.exp & 2)) {
 #pragma unroll
-            for (int kh = 0; kh < K; ++kh) {
-              const int slot = cmod(u + P - kh, K);          // output row r + P - kh; kh = 0 opens it (C = 0)
+          for (int kh = 0; kh < K; ++kh) {
+            const int slot = cmod(u + P - kh, K);          // output row r + P - kh; kh = 0 opens it (C = 0)
 #pragma unroll
-              for (int c4 = 0; c4 < 4; ++c4) {
-                if (kh == 0) mma16816_z(acc[slot][c4], a[c4], bf[c4][kh][0], bf[c4][kh][1]);
-                else mma16816(acc[slot][c4], a[c4], bf[c4][kh][0], bf[c4][kh][1]);
-              }
+            for (int c4 = 0; c4 < 4; ++c4) {
+              if (kh == 0) mma16816_z(acc[slot][c4], a[c4], bf[c4][kh][0], bf[c4][kh][1]);
+              else mma16816(acc[slot][c4], a[c4], bf[c4][kh][0], bf[c4][kh][1]);
             }
           }
         }
         const int od = r - P;                                // the output row finished by this step
         const int sd = cmod(u - P, K);
-        if (od >= 0 && !(p.exp & 1)) {
+        if (od >= 0) {
           uint8_t* ob = ost + (od & 1) * kOst;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {                      // i = odd column | tile << 1
@@ -591,7 +588,6 @@ static Cfg make_cfg(int kind, int B, int C, int H, int W, int k) {
   const int fixed = ost + 2 * 12 * 8 + 8 * 8 * 4 + 256;
   int depth = (200 * 1024 - fixed) / c.stage_bytes;
   if (depth > 10) depth = 10;
-  { static const int cap = [] { const char* e = getenv("AN_DWM_DEPTH"); return e ? atoi(e) : 0; }(); if (cap >= 2 && depth > cap) depth = cap; }
   if (depth > H + P) depth = H + P;
   if (depth < 2) depth = 2;
   c.depth = depth;
@@ -635,8 +631,6 @@ static void fill(Params& p, const Cfg& c, int B, int C, int H, int W) {
   p.in_bytes = c.in_bytes; p.stage_bytes = c.stage_bytes; p.in_tx = c.in_tx; p.aux_tx = c.aux_tx;
   p.smem_bytes = static_cast<int>(c.smem) & ~15;
   p.ragged = c.ragged ? 1 : 0;
-  static const int exp = [] { const char* e = getenv("AN_DWM_EXP"); return e ? atoi(e) : 0; }();
-  p.exp = exp;
 }
 
 static int xf_mode(const float* scale, int act) {
