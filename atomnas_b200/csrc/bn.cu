@@ -208,7 +208,7 @@ __global__ void bn_bwd_finalize_multi_kernel(const __grid_constant__ BnSegs sg, 
 // out = act(a1[c]*x1 + a2[c]*x2 + a3[c]); a1/a2 default 1, a3 default 0, x2 optional.
 // A thread owns ONE 8-channel group (its coefficients stay in registers) and walks rows with a
 // stride; 4 rows are in flight per thread (loads issued before the first use).
-constexpr int kAffUnroll = 4;
+constexpr int kAffUnroll = 4;       // rows in flight per thread; measured 1 / 2 / 4 / 8: 1.51 / 1.18 / 1.16 / 1.33 ms over the sweep
 __device__ __forceinline__ uint4 affine8(const uint4 v, const uint4 w, const bool two, const float* c1,
                                          const float* c2, const float* c3, const int act) {
   const uint32_t vi[4] = {v.x, v.y, v.z, v.w}, wi[4] = {w.x, w.y, w.z, w.w};
