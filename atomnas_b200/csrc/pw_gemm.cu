@@ -38,6 +38,15 @@ constexpr int kMaxStaging = 4;            // staged output (and operand) tiles a
 constexpr int kBarBytes = 384;
 constexpr int kAuxBytes = kBarBytes + 4 * 2 * kMaxBN * 4 + 2 * kMaxGroupCols * 4 + kMaxBN * 8;
 
+// Diagnostic build only (-DAN_GEMM_TRACE): per-tile clock stamps of the TMA producer, the store / statistics thread
+// and epilogue warp 6 of CTA (0,0), printed by that CTA when it finishes.
+#ifdef AN_GEMM_TRACE
+__device__ unsigned int g_gemm_trace[3][64][8];
+#define AN_GT(role, slot) do { if (blockIdx.x == 0 && blockIdx.y == 0 && tc < 64) g_gemm_trace[role][tc][slot] = static_cast<unsigned int>(clock64()); } while (0)
+#else
+#define AN_GT(role, slot) do { } while (0)
+#endif
+
 struct GemmDev {
   CUtensorMap tm_x1, tm_x2, tm_w, tm_y, tm_r;
   int M, N, K;
@@ -56,6 +65,7 @@ struct GemmDev {
   int r_act;
   // staged epilogue (bf16 output, no bias): tile -> swizzled smem -> TMA store; BN partials by MMA
   int staged, nbuf, ytile_bytes, off_y, off_r, off_ones, off_aux;
+  int resident, off_w;   // weight tiles of the CTA's column group stay in shared memory (plain A operand, K <= 64)
 };
 
 // In-place prologue on one 16-byte chunk (8 channels) of a swizzled operand tile.
@@ -117,7 +127,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pw_gemm_kernel(const __grid_c
     if (lane == 0) {
       for (int s = 0; s < S; ++s) {
         mbar_init(&full[s], 1);
-        mbar_init(&xf[s], 8);                  // one elected arrival per prologue warp
+        mbar_init(&xf[s], p.resident ? 1 : 8);   // one elected arrival per prologue warp (resident mode: xf[0] = weights landed)
         mbar_init(&empty[s], 1);
       }
       for (int b = 0; b < 2; ++b) {
@@ -148,31 +158,70 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pw_gemm_kernel(const __grid_c
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (lane == 0 && p.resident) {
+      // Resident mode (expand forward / projection dgrad of the wide layers: K <= 64, plain A operand).  The
+      // TMA unit sustains only ~0.3 box rows per clock (measured), and a 128 x 128 tile costs
+      // 256 store rows (+ 256 rows of the saved raw tensor): reloading the 128 A rows and 128 weight rows
+      // for every column tile of an M tile was 40 % of the rows.  Here the group's weight tiles are
+      // loaded once per CTA and the A tile once per M tile.
       uint32_t it = 0, tc = 0;
-      const uint32_t tx = static_cast<uint32_t>(a_bytes + p.block_n * 128);
-      for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x)
+      const int ntl = nt_end - nt_begin;
+      mbar_expect_tx(&xf[0], static_cast<uint32_t>(ntl * p.block_n * 128));
+      for (int j = 0; j < ntl; ++j)
+        tma_load_2d(smem + p.off_w + j * kTileB, &p.tm_w, &xf[0], 0, (nt_begin + j) * p.block_n);
+      for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x, ++it) {
+        const int s = it % S;
+        mbar_wait(&empty[s], ((it / S) & 1) ^ 1);
+        mbar_expect_tx(&full[s], static_cast<uint32_t>(kTileA));
+        tma_load_2d(smem + s * kTileA, &p.tm_x1, &full[s], 0, mt * kBM);
         for (int nt = nt_begin; nt < nt_end; ++nt, ++tc) {
-          if (has_r) {                       // epilogue operand tile (saved raw tensor / residual)
+          AN_GT(0, 0);
+          if (has_r) {
             const int rb = tc % p.nbuf;
             const int ncol0 = nt * p.block_n;
             const int ng = min(p.block_n / 64, (p.N - ncol0 + 63) / 64);
             mbar_wait(&rempty[rb], ((tc / p.nbuf) & 1) ^ 1);
+            AN_GT(0, 1);
             mbar_expect_tx(&rfull[rb], static_cast<uint32_t>(ng * kGroupBytes));
             for (int gq = 0; gq < ng; ++gq)
               tma_load_2d(smem + p.off_r + rb * p.ytile_bytes + gq * kGroupBytes, &p.tm_r, &rfull[rb],
                           ncol0 + gq * 64, mt * kBM);
           }
+          AN_GT(0, 2);
+          AN_GT(0, 3);
+          AN_GT(0, 4);
+        }
+      }
+    } else if (lane == 0) {
+      uint32_t it = 0, tc = 0;
+      const uint32_t tx = static_cast<uint32_t>(a_bytes + p.block_n * 128);
+      for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x)
+        for (int nt = nt_begin; nt < nt_end; ++nt, ++tc) {
+          AN_GT(0, 0);
+          if (has_r) {                       // epilogue operand tile (saved raw tensor / residual)
+            const int rb = tc % p.nbuf;
+            const int ncol0 = nt * p.block_n;
+            const int ng = min(p.block_n / 64, (p.N - ncol0 + 63) / 64);
+            mbar_wait(&rempty[rb], ((tc / p.nbuf) & 1) ^ 1);
+            AN_GT(0, 1);
+            mbar_expect_tx(&rfull[rb], static_cast<uint32_t>(ng * kGroupBytes));
+            for (int gq = 0; gq < ng; ++gq)
+              tma_load_2d(smem + p.off_r + rb * p.ytile_bytes + gq * kGroupBytes, &p.tm_r, &rfull[rb],
+                          ncol0 + gq * 64, mt * kBM);
+          }
+          AN_GT(0, 2);
           for (int kb = 0; kb < kblocks; ++kb, ++it) {
             const int s = it % S;
             const uint32_t ph = (it / S) & 1;
             mbar_wait(&empty[s], ph ^ 1);
+            if (kb == 0) AN_GT(0, 3);
             mbar_expect_tx(&full[s], tx);
             uint8_t* st = smem + s * stage_bytes;
             tma_load_2d(st, &p.tm_x1, &full[s], kb * kBK, mt * kBM);
             if (p.a_mode == 2) tma_load_2d(st + kTileA, &p.tm_x2, &full[s], kb * kBK, mt * kBM);
             tma_load_2d(st + a_bytes, &p.tm_w, &full[s], kb * kBK, nt * p.block_n);
           }
+          AN_GT(0, 4);
         }
     } else if (lane == 1 && p.staged) {
       // -------------------------------------------------------------- tile store / statistics issuer
@@ -189,11 +238,25 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pw_gemm_kernel(const __grid_c
           const int ncols_valid = min(p.block_n, p.N - ncol0);
           uint8_t* yt = smem + p.off_y + yb * p.ytile_bytes;
           const uint8_t* rt = smem + p.off_r + yb * p.ytile_bytes;
+          AN_GT(1, 0);
           mbar_wait(&yfull[yb], yph);
+          AN_GT(1, 1);
           const int ng = (ncols_valid + 63) / 64;
           for (int gq = 0; gq < ng; ++gq)
             tma_store_2d(&p.tm_y, yt + gq * kGroupBytes, ncol0 + gq * 64, mt * kBM);
           tma_store_commit();
+          AN_GT(1, 2);
+          // keep nbuf - 1 stores in flight: the store issued nbuf - 1 tiles ago has read its smem (a 32 KiB tile
+          // store occupies the TMA unit for ~2000 clk).  The buffer is handed back BEFORE the statistics MMAs are
+          // issued: measured, the epilogue waiting for a free staging tile costs more than its (deferred) read of
+          // the statistics waiting for the MMAs (expand forward 1.77 vs 1.96 ms over the sweep).
+          switch (p.nbuf) {
+            case 4: tma_store_wait_read<3>(); break;
+            case 3: tma_store_wait_read<2>(); break;
+            case 2: tma_store_wait_read<1>(); break;
+            default: tma_store_wait_read<0>(); break;
+          }
+          if (tc + 1 >= static_cast<uint32_t>(p.nbuf)) mbar_arrive(&yempty[(tc + 1 - p.nbuf) % p.nbuf]);
           if (want_stats) {
             tc_fence_after();
             const uint32_t a_addr = smem_u32(yt);
@@ -214,22 +277,35 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pw_gemm_kernel(const __grid_c
           } else if (has_r) {
             mbar_arrive(&rempty[yb]);                       // every epilogue thread is past its reads
           }
-          // keep nbuf - 1 stores in flight: the store issued nbuf - 1 tiles ago has read its smem.
-          // (HBM write latency x bandwidth needs > 64 KB in flight per SM: 2 staging tiles cap a
-          // store-bound GEMM at ~40 % of the HBM roof, 4 tiles lift that)
-          switch (p.nbuf) {
-            case 4: tma_store_wait_read<3>(); break;
-            case 3: tma_store_wait_read<2>(); break;
-            case 2: tma_store_wait_read<1>(); break;
-            default: tma_store_wait_read<0>(); break;
-          }
-          if (tc + 1 >= static_cast<uint32_t>(p.nbuf)) mbar_arrive(&yempty[(tc + 1 - p.nbuf) % p.nbuf]);
+          AN_GT(1, 4);
         }
       tma_store_wait<0>();
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (lane == 0 && p.resident) {
+      uint32_t it = 0, tc = 0;
+      const uint32_t idesc = umma_idesc_bf16(kBM, p.block_n, 0, 0);
+      const int nk = min(4, (p.K + 15) / 16);
+      mbar_wait(&xf[0], 0);                      // the group's weight tiles
+      for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x, ++it) {
+        const int s = it % S;
+        mbar_wait(&full[s], (it / S) & 1);
+        const uint32_t a_addr = smem_u32(smem + s * kTileA);
+        for (int nt = nt_begin; nt < nt_end; ++nt, ++tc) {
+          const uint32_t buf = tc & 1, tph = (tc >> 1) & 1;
+          mbar_wait(&tempty[buf], tph ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * kMaxBN;
+          const uint32_t b_addr = smem_u32(smem + p.off_w + (nt - nt_begin) * kTileB);
+          for (int k = 0; k < nk; ++k)
+            umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32, 16, 1024), umma_desc_sw128(b_addr + k * 32, 16, 1024), idesc,
+                      k > 0 ? 1u : 0u);
+          if (nt == nt_end - 1) umma_commit(&empty[s]);
+          umma_commit(&tfull[buf]);
+        }
+      }
+    } else if (lane == 0) {
       uint32_t it = 0, tc = 0;
       const uint32_t idesc = umma_idesc_bf16(kBM, p.block_n, 0, 0);
       for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x)
@@ -320,6 +396,29 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pw_gemm_kernel(const __grid_c
       const float lo = (p.r_act == ACT_RELU || p.r_act == ACT_RELU6) ? 0.f : -INFINITY;
       const float hi = (p.r_act == ACT_RELU6) ? 6.f : INFINITY;
       float4* colpar4 = reinterpret_cast<float4*>(colpar);          // per column PAIR: {s0, s1, h0, h1}
+      int prev_gc = 0, prev_valid = 0;
+      auto read_stats = [&](uint32_t t, int gc, int nvalid) {
+        mbar_wait(sfull, t & 1);
+        __syncwarp();
+        tc_fence_after();
+        const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        if (nhalves == 1 || half == 1) {                 // column sums
+          const float s1 = tmem_ld1(t_lane + kTmemStat2);
+          if (et < nvalid) stat_acc[gc] += s1;
+        }
+        if ((nhalves == 1 || half == 0) && q * 32 < p.block_n) {   // diagonal of D1
+          float d[32];
+          tmem_ld32(t_lane + kTmemStat1 + q * 32, d);
+#pragma unroll
+          for (int b = 16; b >= 1; b >>= 1) {
+            const bool up = (lane & b) != 0;
+#pragma unroll
+            for (int i = 0; i < b; ++i) d[i] = up ? d[i + b] : d[i];
+          }
+          if (et < nvalid) stat_acc[kMaxGroupCols + gc] += d[0];
+        }
+        tc_fence_before();
+      };
       uint32_t tc = 0;
       for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x)
         for (int nt = nt_begin; nt < nt_end; ++nt, ++tc) {
@@ -342,9 +441,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pw_gemm_kernel(const __grid_c
             }
             named_bar_sync(1, n_epi);
           }
+          if (warp == 6 && lane == 0) AN_GT(2, 0);
           if (has_r) mbar_wait(&rfull[yb], yph);
+          if (warp == 6 && lane == 0) AN_GT(2, 1);
           mbar_wait(&yempty[yb], yph ^ 1);       // the store that last used this staging buffer is done
+          if (warp == 6 && lane == 0) AN_GT(2, 2);
           mbar_wait(&tfull[buf], tph);
+          if (warp == 6 && lane == 0) AN_GT(2, 3);
           tc_fence_after();
           const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kMaxBN;
           if (c_begin >= c_end) {                // ragged tile: nothing to drain for this half
@@ -398,33 +501,21 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pw_gemm_kernel(const __grid_c
               *reinterpret_cast<uint4*>(yt + goff + phys) = make_uint4(o[0], o[1], o[2], o[3]);
             }
           }
+          if (warp == 6 && lane == 0) AN_GT(2, 4);
+          // Statistics of the PREVIOUS tile: its MMAs were issued when that tile was handed over and have
+          // long finished while this tile was drained (waiting for them right after the hand-over cost
+          // ~1800 clk per tile: profiles/r02_gemm_tiletrace_*_before.txt).  They are read before this
+          // tile's hand-over, so the store thread cannot overwrite the statistics columns earlier.
+          if (want_stats && tc > 0) read_stats(tc - 1, prev_gc, prev_valid);
+          prev_gc = (nt - nt_begin) * p.block_n + et;
+          prev_valid = ncols_valid;
           fence_proxy_async_smem();              // tile (generic-proxy writes) -> TMA store / UMMA reads
           __syncwarp();
           if (lane == 0) mbar_arrive(&yfull[yb]);     // one arrival per warp: per-thread arrivals serialise
-          if (want_stats) {
-            mbar_wait(sfull, tc & 1);
-            __syncwarp();
-            tc_fence_after();
-            const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-            const int gc = (nt - nt_begin) * p.block_n + et;
-            if (nhalves == 1 || half == 1) {                 // column sums
-              const float s1 = tmem_ld1(t_lane + kTmemStat2);
-              if (et < ncols_valid) stat_acc[gc] += s1;
-            }
-            if ((nhalves == 1 || half == 0) && q * 32 < p.block_n) {   // diagonal of D1
-              float d[32];
-              tmem_ld32(t_lane + kTmemStat1 + q * 32, d);
-#pragma unroll
-              for (int b = 16; b >= 1; b >>= 1) {
-                const bool up = (lane & b) != 0;
-#pragma unroll
-                for (int i = 0; i < b; ++i) d[i] = up ? d[i + b] : d[i];
-              }
-              if (et < ncols_valid) stat_acc[kMaxGroupCols + gc] += d[0];
-            }
-            tc_fence_before();
-          }
+          if (warp == 6 && lane == 0) AN_GT(2, 5);
+          if (warp == 6 && lane == 0) AN_GT(2, 6);
         }
+      if (want_stats && tc > 0) read_stats(tc - 1, prev_gc, prev_valid);
       if (want_stats) {
         named_bar_sync(1, n_epi);
         const int gcols = (nt_end - nt_begin) * p.block_n;
@@ -533,6 +624,18 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pw_gemm_kernel(const __grid_c
 
   tc_fence_before();
   __syncthreads();
+#ifdef AN_GEMM_TRACE
+  if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
+    unsigned int (*g)[64][8] = g_gemm_trace;
+    for (int t = 8; t < 28; ++t)
+      printf("tile %2d | producer: period %5u wait-rempty %5u issue-r %5u wait-empty %5u issue-AB %5u | store: period %5u wait-yfull %5u "
+             "issue-store %5u stats-mma %5u wait-read %5u | epi: period %5u wait-rfull %5u wait-yempty %5u wait-tfull %5u drain %5u arrive %5u stats %5u\n",
+             t, g[0][t][0] - g[0][t - 1][0], g[0][t][1] - g[0][t][0], g[0][t][2] - g[0][t][1], g[0][t][3] - g[0][t][2], g[0][t][4] - g[0][t][3],
+             g[1][t][0] - g[1][t - 1][0], g[1][t][1] - g[1][t][0], g[1][t][2] - g[1][t][1], g[1][t][3] - g[1][t][2], g[1][t][4] - g[1][t][3],
+             g[2][t][0] - g[2][t - 1][0], g[2][t][1] - g[2][t][0], g[2][t][2] - g[2][t][1], g[2][t][3] - g[2][t][2], g[2][t][4] - g[2][t][3],
+             g[2][t][5] - g[2][t][4], g[2][t][6] - g[2][t][5]);
+  }
+#endif
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -868,6 +971,19 @@ extern "C" int an_pw_gemm(const an_pw_gemm_args* a, void* stream) {
     if (getenv("AN_PW_NBUF") != nullptr) { const int e = atoi(getenv("AN_PW_NBUF")); if (e >= 1 && e < nb) nb = e; }
     d.nbuf = nb;
   }
+  // resident weights: plain A operand, one k-block, the column group's weight tiles + 2 A stages + two staged
+  // tiles fit (AN_PW_RESIDENT=0 switches it off for A/B runs)
+  {
+    static const bool allow = [] { const char* e = getenv("AN_PW_RESIDENT"); return e == nullptr || e[0] != '0'; }();
+    const int per_buf = d.ytile_bytes * (has_r ? 2 : 1);
+    const int need = 2 * kTileA + g.tiles_per_group * kTileB + 2 * per_buf + kGroupBytes + kAuxBytes + 1024;
+    d.resident = (allow && d.staged && a->a_mode == 0 && a->K <= kBK && need <= 227 * 1024) ? 1 : 0;
+    if (d.resident) {
+      int nb = (227 * 1024 - (need - 2 * per_buf)) / per_buf;
+      if (nb > kMaxStaging) nb = kMaxStaging;
+      d.nbuf = nb < 2 ? 2 : nb;                  // what fits next to the resident weights (>= 2 by `need`)
+    }
+  }
   int fixed = 0;
   if (d.staged) {
     if (int e = make_tmap_bf16_2d(&d.tm_y, a->y, a->N, a->M, a->ldy, 64, kBM)) return e;
@@ -882,10 +998,16 @@ extern "C" int an_pw_gemm(const an_pw_gemm_args* a, void* stream) {
     if (a->stats_part != nullptr) fixed += kGroupBytes;
   }
   const int budget = 227 * 1024 - 1024 - kAuxBytes - fixed;
-  d.stages = budget / stage_bytes;
-  if (d.stages > 4) d.stages = 4;
-  AN_REQUIRE(d.stages >= 2, "an_pw_gemm: shared-memory budget too small (%d B for stages)", budget);
-  d.off_y = d.stages * stage_bytes;
+  if (d.resident) {
+    d.stages = 2;                                // A tiles only (one per M tile); the weight tiles follow them
+    d.off_w = d.stages * kTileA;
+    d.off_y = d.off_w + g.tiles_per_group * kTileB;
+  } else {
+    d.stages = budget / stage_bytes;
+    if (d.stages > 4) d.stages = 4;
+    AN_REQUIRE(d.stages >= 2, "an_pw_gemm: shared-memory budget too small (%d B for stages)", budget);
+    d.off_y = d.stages * stage_bytes;
+  }
   d.off_r = d.off_y + (d.staged ? d.nbuf * d.ytile_bytes : 0);
   d.off_ones = d.off_r + (has_r ? d.nbuf * d.ytile_bytes : 0);
   d.off_aux = d.off_ones + ((d.staged && a->stats_part != nullptr) ? kGroupBytes : 0);
