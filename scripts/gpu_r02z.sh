@@ -8,7 +8,7 @@ mkdir -p gpurun_out
 [ -f atomnas_b200/libatomnas_b200_trace.so ] || { echo "build atomnas_b200/libatomnas_b200_trace.so first (see header)"; exit 1; }
 cp atomnas_b200/libatomnas_b200.so /tmp/orig.so
 cp atomnas_b200/libatomnas_b200_trace.so atomnas_b200/libatomnas_b200.so
-for w in project_dgrad expand_fwd expand_fwd_nostats; do
+for w in ${2:-project_dgrad expand_fwd expand_fwd_nostats project_fwd expand_dgrad}; do
   echo "== trace $w"
   timeout 120 python scripts/trace_gemm.py $w 2>&1 | tail -20 > gpurun_out/${tag}_gemm_trace_$w.txt
   sed -n '6,10p' gpurun_out/${tag}_gemm_trace_$w.txt

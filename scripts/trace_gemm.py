@@ -15,6 +15,13 @@ if which == "project_dgrad":
 elif which == "expand_fwd":
     x = torch.randn(M, cin, device="cuda").to(BF); we = torch.randn(Kh, cin, device="cuda").to(BF); e = torch.empty(M, Kh, device="cuda", dtype=BF)
     f = lambda: K.pw_gemm(x, we, e, M, Kh, cin, stats_part=part)
+elif which == "project_fwd":
+    d = torch.randn(M, Kh, device="cuda").to(BF); wp = torch.randn(cout, Kh, device="cuda").to(BF); pr = torch.empty(M, cout, device="cuda", dtype=BF)
+    f = lambda: K.pw_gemm(d, wp, pr, M, cout, Kh, a_mode=1, a_act=1, a1=v, a3=z, stats_part=part)
+elif which == "expand_dgrad":
+    e = torch.randn(M, Kh, device="cuda").to(BF); e2 = torch.randn(M, Kh, device="cuda").to(BF); weT = torch.randn(cin, Kh, device="cuda").to(BF)
+    x = torch.empty(M, cin, device="cuda", dtype=BF)
+    f = lambda: K.pw_gemm(e, weT, x, M, cin, Kh, x2=e2, a_mode=2, a1=v, a2=z, a3=z)
 else:
     x = torch.randn(M, cin, device="cuda").to(BF); we = torch.randn(Kh, cin, device="cuda").to(BF); e = torch.empty(M, Kh, device="cuda", dtype=BF)
     f = lambda: K.pw_gemm(x, we, e, M, Kh, cin)
