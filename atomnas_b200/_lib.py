@@ -88,6 +88,7 @@ SIGNATURES = {
     "an_dw_bwd_data_stats_rows": (c_int, [c_int] * 7),
     "an_dw_bwd_weight": (c_int, [ctypes.POINTER(DwBwdArgs), c_fp, c_fp, c_vp]),
     "an_dw_bwd_weight_rows": (c_int, [c_int] * 7),
+    "an_dw_on_tensor_cores": (c_int, [c_int] * 5),
     "an_bn_finalize": (c_int, [c_fp, c_int, c_int, c_d, c_fp, c_fp, c_fp, c_fp, c_f, c_f, c_fp,
                                c_fp, c_fp, c_fp, c_vp]),
     "an_bn_bwd_finalize": (c_int, [c_fp, c_int, c_int, c_d, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp,

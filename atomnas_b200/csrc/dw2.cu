@@ -861,6 +861,10 @@ static inline void out_hw(int H, int W, int k, int s, int* Ho, int* Wo) {
   *Wo = (W + 2 * P - k) / s + 1;
 }
 
+extern "C" int an_dw_on_tensor_cores(int which, int k, int stride, int B, int W) {
+  return (which == 0 ? dwm::use_conv(k, stride, B, W) : dwm::use_wgrad(k, stride, B, W)) ? 1 : 0;
+}
+
 extern "C" int an_dw_fwd_stats_rows(int B, int C, int Ho, int Wo, int k, int stride, int /*fused*/) {
   if (dwm::use_conv(k, stride, B, Wo)) return dwm::fwd_rows(B, C, Ho, Wo, k);
   return dw2::make_cfg(0, B, C, Ho, Wo, Ho * stride, k, stride).parts;

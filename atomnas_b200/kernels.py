@@ -111,6 +111,12 @@ def dw_bwd_data(g, draw, eraw, ge, w, ca, cb, cc, e_scale, e_shift, e_mean, e_rs
     L.check(L.lib().an_dw_bwd_data(a, L.stream_ptr()), "an_dw_bwd_data")
 
 
+def dw_on_tensor_cores(which, k, stride, B, W):
+    """Dispatch rule of the depthwise kernels (host logic only, no GPU needed): which = 0 forward /
+    data gradient, 1 weight gradient."""
+    return bool(L.lib().an_dw_on_tensor_cores(which, k, stride, B, W))
+
+
 def dw_bwd_weight_rows(B, C, H, W, k, stride, fused=True):
     return L.lib().an_dw_bwd_weight_rows(B, C, H, W, k, stride, 1 if fused else 0)
 

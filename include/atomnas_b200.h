@@ -157,6 +157,10 @@ int an_dw_bwd_data(const an_dw_bwd_args* args, void* stream);
 int an_dw_bwd_data_stats_rows(int B, int C, int H, int W, int k, int stride, int fused);
 int an_dw_bwd_weight(const an_dw_bwd_args* args, float* partials, float* dw, void* stream);
 int an_dw_bwd_weight_rows(int B, int C, int H, int W, int k, int stride, int fused);
+/* 1 if the (k, stride, batch, map width W of the stride-1 layer) shape runs on the tensor cores:
+ * which = 0 forward / data gradient (bf16 operand + taps -- the oracle's bf16 points follow this rule),
+ * which = 1 weight gradient. */
+int an_dw_on_tensor_cores(int which, int k, int stride, int B, int W);
 
 /* ------------------------------------------------------------------------------------------
  * BatchNorm2d (training mode) pieces -- nn.BatchNorm2d at models/mobilenet_base.py:142, :342.

@@ -281,3 +281,19 @@ def test_fused_block_surface_matches_reference_state_dict(name):
     assert list(blk.get_named_depthwise_bn("p").keys()) == ["p.depth_ops.%d.1.1" % i for i in range(len(a["channels"]))]
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         blk(g["x"])
+
+
+def test_oracle_bf16_points_follow_the_depthwise_dispatch_rule():
+    """The oracle rounds the depthwise operand and taps to bf16 exactly on the layers the engine's forward
+    runs on the tensor cores (host-side rule of the C-ABI library; no kernel is launched)."""
+    from atomnas_b200 import kernels as K
+    from oracle import atomnas_oracle as O
+    if os.environ.get("AN_DW_MMA") is not None:
+        pytest.skip("dispatch forced by AN_DW_MMA")
+    for k in (3, 5, 7):
+        for stride in (1, 2):
+            for B in (1, 4, 8, 16, 256):
+                for W in (4, 7, 8, 14, 28, 56, 112):
+                    assert K.dw_on_tensor_cores(0, k, stride, B, W) == O.dw_on_tensor_cores(k, stride, B, W), (k, stride, B, W)
+                    if stride == 2 or B < 8:
+                        assert not K.dw_on_tensor_cores(1, k, stride, B, W)
