@@ -63,6 +63,15 @@ def test_committed_series_lines():
         assert g["impl"] == "reference-gpu" and g["value"] > 0 and base["value"] / g["value"] > 3.0
 
 
+def test_committed_multi_gpu_line():
+    base, d = last_line("r02_bench_n1.json"), last_line("r02_bench_n8.json")
+    assert d["n_gpus"] == 8 and d["scaling"] == "weak" and d["config"]["global_batch"] == 8 * 256
+    assert d["config"]["parallelism"] == "dp8" and d["gpu_launches"] > 0 and d["e2e"]["value"] > 0
+    assert 0.95 <= d["value"] / (8 * base["value"]) <= 1.02          # weak scaling: max over ranks of the step time
+    r = last_line("r02_bench_reference_n8.json")
+    assert r["impl"] == "reference" and r["value"] > 0 and r["e2e"]["h2d_bytes_per_step"] == 0
+
+
 def test_bench_defaults_and_workload():
     import bench
     assert bench.PER_GPU_BATCH == 256 and bench.IMAGE == 224
